@@ -1,0 +1,64 @@
+// Shared helpers for the iq_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace iq {
+
+// ---- error plumbing: every extern "C" entry returns 0 or a negative code and
+// leaves a message retrievable through iq_last_error().
+void set_error(const std::string &msg);
+const char *last_error();
+
+#define IQ_CHECK(cond, msg)                                                                        \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            ::iq::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+#define IQ_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::iq::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " +        \
+                            cudaGetErrorString(_e));                                               \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+#define IQ_LAUNCH_CHECK() IQ_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+#define IQ_COUNT_LAUNCH() (++::iq::g_launch_count)
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+
+__device__ __forceinline__ float apply_act(float v, int act)
+{
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
+    return v;
+}
+
+// monotone float -> uint key (larger float <=> larger uint); -0.0 sorts just below +0.0
+__device__ __forceinline__ uint32_t ordered_u32(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_u32(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+}  // namespace iq

@@ -1,0 +1,61 @@
+// Internal launch functions shared between translation units of libiq_b200.
+#pragma once
+#include "common.cuh"
+
+namespace iq {
+
+// coalition.cu
+int launch_mask_shapley(const float *data, const float *center, const int64_t *orders, const int64_t *region_id,
+                        int64_t bs, int64_t R, int64_t N, float *out, bool in_place, cudaStream_t st);
+int launch_mask_interaction(const float *data, const float *center, const int64_t *contexts, int64_t ctx, int64_t m,
+                            int64_t region_i, int64_t region_j, const int64_t *region_id, int64_t R, int64_t N,
+                            int point_major, float *out, cudaStream_t st);
+int launch_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v, cudaStream_t st);
+int launch_shapley_accumulate(const float *v, const int64_t *orders, int64_t bs, int64_t R, double *phi_sum,
+                              cudaStream_t st);
+int launch_interaction_reduce(const float *logits, int64_t P, int64_t ctx, int64_t C, int64_t lbl, int softmax_normal,
+                              double *out, cudaStream_t st);
+
+// geometry.cu
+int launch_fps(const float *xyz, int64_t B, int64_t N, int64_t npoint, int64_t *idx64, int32_t *idx32, float *new_xyz,
+               cudaStream_t st);
+int launch_region_id(const float *xyz, const int64_t *fps_index, int64_t N, int64_t R, int64_t *region_id,
+                     cudaStream_t st);
+int launch_square_distance3(const float *src, const float *dst, int64_t B, int64_t N, int64_t M, float *out,
+                            cudaStream_t st);
+int launch_center(const float *xyz, int64_t N, float *center, cudaStream_t st);
+
+// sgemm.cu
+struct GemmDesc {
+    const float *A = nullptr;      // (M,K) row-major, leading dimension lda
+    const float *B = nullptr;      // (N,K) row-major, leading dimension ldb   ->  C = A * B^T
+    float *C = nullptr;            // (M,N) row-major, leading dimension ldc (may be null in pool mode)
+    int64_t lda = 0, ldb = 0, ldc = 0;
+    int64_t strideA = 0, strideB = 0, strideC = 0, strideBias = 0;   // per batch element
+    int M = 0, N = 0, K = 0, batch = 1;
+    float alpha = 1.0f;
+    const float *bias = nullptr;   // per output column n (length N), may be null
+    const float *row_bias = nullptr;  // optional (M/row_group, N) addend indexed by m / row_group
+    int row_group = 1;
+    int64_t ld_row_bias = 0;
+    int act = ACT_NONE;
+    // pooling epilogue: per (m-tile of 128 rows, n) partial max / argmax / sum over the tile's rows
+    float *pool_max = nullptr;     // (ceil(M/128), N)
+    int32_t *pool_arg = nullptr;   // optional, row index (within the whole M) of the max, lowest on ties
+    float *pool_sum = nullptr;     // optional
+};
+int launch_sgemm(const GemmDesc &g, cudaStream_t st);
+int launch_pool_finish(const float *pmax, const int32_t *parg, const float *psum, int64_t groups, int tiles_per_group,
+                       int rows_per_group, int N, float *out_max, int64_t ld_max, int64_t *out_arg, float *out_mean,
+                       int64_t ld_mean, cudaStream_t st);
+
+// graph.cu
+int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int k, int32_t *idx, cudaStream_t st);
+int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx,
+                     cudaStream_t st);
+int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st);
+int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
+                      int act, float *out, int64_t ldo, float *neg_sqnorm, cudaStream_t st);
+int launch_xyz_to_point_major(const float *x_cf, int64_t B, int64_t N, float *x_pm, cudaStream_t st);
+
+}  // namespace iq

@@ -1,0 +1,199 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):   python tests/golden/make_golden.py [names...]
+
+The reference ships no tests or golden vectors, so these
+fixtures are outputs of the reference's own functions on the synthetic inputs of
+interpret_quality_b200/synthetic.py:
+
+  geometry.npz      farthest_point_sample, cal_region_id, generate_all_orders,
+                    mask_data_batch, the interaction mask block, square_distance,
+                    query_ball_point, in-model FPS on a masked cloud
+  <model>.npz       logits of masked clouds, shap_sampling_all_regions_batch,
+                    compute_order_interaction_logits, compute_order_interaction,
+                    get_reward (both softmax types), cal_norm_factor
+
+The fixtures pin oracle/ (tests/test_oracle_golden.py, CPU) and the CUDA path
+(tests/test_gpu_*.py).
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("INTERPRET_QUALITY_REF", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+os.chdir(REF)
+
+from interpret_quality_b200 import synthetic  # noqa: E402
+
+import final_save_fps as ref_fps  # noqa: E402
+import final_shapley_value as ref_sv  # noqa: E402
+import final_point_binary_interaction_logits as ref_il  # noqa: E402
+import final_cal_interactions as ref_ci  # noqa: E402
+from tools import final_common as ref_common  # noqa: E402
+from tools import final_util as ref_util  # noqa: E402
+from models import pointnet2 as ref_pn2  # noqa: E402
+from models import pointconv as ref_pc  # noqa: E402
+from models import dgcnn as ref_dg  # noqa: E402
+
+R = 32
+LBL = 3
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def base_inputs(N):
+    data = torch.from_numpy(synthetic.make_cloud(N))
+    fps_idx = ref_fps.farthest_point_sample(data, R)[0].numpy()
+    region_id = ref_sv.cal_region_id(data, fps_idx, None, save=False)
+    return data, fps_idx, region_id
+
+
+def geometry():
+    out = {}
+    for N in (1024, 2048):
+        data, fps_idx, region_id = base_inputs(N)
+        out["fps_idx_%d" % N] = fps_idx
+        out["region_id_%d" % N] = region_id
+    data, fps_idx, region_id = base_inputs(1024)
+    # seed replay of the permutations (final_shapley_value.py:59-72 after set_random(1))
+    ref_util.set_random(1)
+    a = types.SimpleNamespace(num_samples_save=1000, num_regions=R)
+    orders = ref_sv.generate_all_orders(None, a, save=False)
+    out["orders_sha1"] = np.array(sha(orders.astype(np.int64)))
+    out["orders_head"] = orders[:8]
+    # pairs (final_gen_pair.py:288-300 after set_random(1))
+    import final_gen_pair as ref_gp
+    ref_util.set_random(1)
+    out["pairs_head"] = ref_gp.gen_pair_random(types.SimpleNamespace(num_regions=R, num_pairs_random=300))[:8]
+    # Shapley masks
+    center = torch.mean(data, dim=1).squeeze()
+    out["center"] = center.numpy()
+    bs = 3
+    a = types.SimpleNamespace(num_regions=R)
+    md = data.expand((R + 1) * bs, 1024, 3).clone()
+    md = ref_common.mask_data_batch(md, center, orders[:bs], region_id, a)
+    out["mask_shapley_sha1"] = np.array(sha(md.numpy()))
+    out["mask_shapley_rows"] = md.numpy()[[0, 1, 17, 32, 33, 40, 98]]
+    out["mask_shapley_row_ids"] = np.array([0, 1, 17, 32, 33, 40, 98])
+    # single-permutation form (final_shapley_value.py:74-88)
+    md1 = data.expand(R + 1, 1024, 3).clone()
+    md1 = ref_sv.mask_data(md1, center, orders[0], region_id)
+    assert torch.equal(md1, md[:R + 1])
+    # interaction mask block (final_point_binary_interaction_logits.py:42-56), captured through a probe model
+    pairs, contexts = synthetic.make_pairs_and_contexts(2, R, orders_m=(0, 3, 30), max_contexts=4)
+    for m in (0, 3, 30):
+        seen = []
+
+        class Probe(torch.nn.Module):
+            def forward(self, x):
+                seen.append(x.clone())
+                return torch.zeros(x.shape[0], 10)
+
+        a = types.SimpleNamespace(interaction_batch_size=3, model="dgcnn")
+        ref_il.compute_order_interaction_logits(Probe(), data, region_id, pairs, contexts[m], a)
+        blk = torch.cat(seen, 0).numpy()
+        out["mask_inter_m%d_sha1" % m] = np.array(sha(blk))
+        out["mask_inter_m%d_shape" % m] = np.array(blk.shape)
+        if m == 3:
+            out["mask_inter_m3_rows"] = blk[:8]
+    out["inter_pairs"] = pairs
+    for m in (0, 3, 30):
+        out["inter_ctx_m%d" % m] = contexts[m].astype(np.int64)
+    # masked cloud -> in-model FPS, square_distance, ball query, knn
+    sparse = md[34:36]                         # permutation 1 rows 1,2: one / two regions kept
+    dense = md[[30, 66]]
+    clouds = torch.cat([sparse, dense, data], 0).contiguous()
+    out["geo_cloud_rows"] = np.array([34, 35, 30, 66, -1])
+    f1 = ref_pn2.farthest_point_sample(clouds, 512)
+    out["fps512"] = f1.numpy().astype(np.int16)
+    new_xyz = ref_pn2.index_points(clouds, f1)
+    f2 = ref_pc.farthest_point_sample(new_xyz, 128)
+    out["fps128"] = f2.numpy().astype(np.int16)
+    sq = ref_pn2.square_distance(new_xyz[:, :64], clouds)
+    out["sqdist_sha1"] = np.array(sha(sq.numpy()))
+    out["sqdist_head"] = sq.numpy()[:, :4, :16]
+    for radius, K in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        gi = ref_pn2.query_ball_point(radius, K, clouds, new_xyz)
+        out["ball_r%d" % int(radius * 10)] = gi.numpy().astype(np.int16)
+    # DGCNN layer-1 kNN sets on xyz (models/dgcnn.py:12-18): sorted member sets only for tie-free rows
+    x = clouds[4:5].permute(0, 2, 1).contiguous()
+    out["knn_xyz_unmasked"] = np.sort(ref_dg.knn(x, 20)[0].numpy(), axis=1).astype(np.int16)
+    np.savez_compressed(os.path.join(HERE, "geometry.npz"), **out)
+    print("geometry.npz written")
+
+
+def load_ref_model(name):
+    args = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True,
+                                 device=torch.device("cpu"))
+    cls = {"pointnet2": ref_util.PointNet2ClsMsg, "pointnet": ref_util.PointNetCls, "dgcnn": ref_util.DGCNN_cls,
+           "gcnn": ref_util.GCNN_cls, "pointconv": ref_util.PointConvDensityClsSsg}[name]
+    m = cls(args)
+    sd = synthetic.make_state_dict(name)
+    assert list(m.state_dict().keys()) == [k for k, _, _ in synthetic.state_dict_spec(name)]
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return m.eval(), args
+
+
+def model_golden(name, N=1024, tag=None):
+    torch.manual_seed(0)
+    model, margs = load_ref_model(name)
+    data, fps_idx, region_id = base_inputs(N)
+    orders = synthetic.make_orders(16, R)
+    lbl = torch.tensor([LBL])
+    out = {"N": np.array(N)}
+    n_perm, bs = (4, 2) if N == 1024 else (1, 1)
+    args = types.SimpleNamespace(num_points=N, num_regions=R, shapley_batch_size=bs, num_samples=n_perm,
+                                 softmax_type="modified", model=name, device=torch.device("cpu"))
+    with torch.no_grad():
+        phi, logits = ref_common.shap_sampling_all_regions_batch(model, data, lbl, region_id, orders, args)
+    out["shapley_phi"] = phi
+    out["shapley_logits"] = logits.numpy()
+    out["shapley_nperm"] = np.array(n_perm)
+    out["reward_modified"] = ref_common.get_reward(logits, lbl, args).numpy()
+    args_n = types.SimpleNamespace(softmax_type="normal")
+    out["reward_normal"] = ref_common.get_reward(logits, lbl, args_n).numpy()
+    # efficiency identity needs v(N) - v(empty)
+    center = torch.mean(data, dim=1).squeeze()
+    with torch.no_grad():
+        out["norm_factor"] = np.array(ref_sv.cal_norm_factor(model, data, lbl, center, None, args, save=False))
+    spread = float(np.abs(logits.numpy() - logits.numpy()[0:1]).max())
+    assert spread > 1e-3 * float(np.abs(logits.numpy()).max()), "degenerate network: logits do not depend on the mask"
+    if N == 1024:
+        pairs, contexts = synthetic.make_pairs_and_contexts(2, R, orders_m=(0, 3, 30), max_contexts=4)
+        iargs = types.SimpleNamespace(interaction_batch_size=3, model=name, softmax_type="modified")
+        for m in (0, 3, 30):
+            with torch.no_grad():
+                il = ref_il.compute_order_interaction_logits(model, data, region_id, pairs, contexts[m], iargs)
+            out["inter_logits_m%d" % m] = il.numpy()
+            out["inter_m%d" % m] = ref_ci.compute_order_interaction(il, lbl, iargs)
+        if name == "pointnet":
+            x = data.permute(0, 2, 1).contiguous()
+            with torch.no_grad():
+                lg, tf, crt = model(x)
+            out["pointnet_trans_feat"] = tf.numpy()
+            out["pointnet_crt"] = crt.numpy().astype(np.int16)
+    fn = os.path.join(HERE, "%s.npz" % (tag or name))
+    np.savez_compressed(fn, **out)
+    print(fn, "written; logits spread", spread, "phi", phi[:4], "norm", out["norm_factor"])
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["geometry", "pointnet", "dgcnn", "gcnn", "pointnet2", "pointconv", "dgcnn_2048"]
+    for n in names:
+        if n == "geometry":
+            geometry()
+        elif n == "dgcnn_2048":
+            model_golden("dgcnn", 2048, "dgcnn_2048")
+        else:
+            model_golden(n)
