@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the coalition-evaluation hot path (BASELINE.json metric: masked-coalition forwards/sec,
+DGCNN k=20, 1024 points, 32 regions, at 1/2/4/8 B200).
+
+One step = one shap_sampling_all_regions_batch call: 100 seed-replayed permutations x 33 masked
+clouds = 3300 forwards through mask -> forward -> reward -> Shapley sums (tools/final_common.py:64-103
+of the reference).  Weak scaling: every rank evaluates its own 100-permutation slice of the 1000 saved
+permutations and the per-region float64 sums are combined by one NCCL allreduce per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--model dgcnn]
+
+Prints ONE JSON line on rank 0 (see the contract in the task description / DESIGN.md section Measurement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R, LBL = 32, 3
+METRIC = "masked-coalition forwards/sec"
+UNIT = "forwards/s"
+
+# algorithmic FLOPs per forward of the as-written reference models (SURVEY.md section 6, 2*MAC)
+MODEL_GFLOP = {"dgcnn": 5.326, "gcnn": 4.789, "pointnet": 0.879, "pointnet2": 7.842, "pointconv": 2.414}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "gcnn", "pointnet"])
+    ap.add_argument("--points", type=int, default=1024)
+    ap.add_argument("--perms", type=int, default=100, help="permutations per step (NUM_SAMPLES of the reference)")
+    ap.add_argument("--chunk", type=int, default=0, help="clouds per internal pass (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(fn):
+        p = json.load(open(fn))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def config_of(a, n_gpus):
+    return {"workload": "%s_k20_shapley_%dperm_x33clouds_N%d_R32" % (a.model, a.perms, a.points),
+            "model_class": {"dgcnn": "DGCNN_cls", "gcnn": "GCNN_cls", "pointnet": "PointNetCls"}[a.model],
+            "num_points": a.points, "num_regions": R, "permutations_per_step_per_gpu": a.perms,
+            "forwards_per_step_per_gpu": a.perms * (R + 1), "parallelism": "perm-shard x%d" % n_gpus,
+            "l2_policy": "256 MiB buffer rewritten between timed steps (flush); per-step working set also exceeds L2",
+            "weights": "seeded trained-like random init (interpret_quality_b200/synthetic.py)"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_inputs(a):
+    from interpret_quality_b200 import synthetic
+    from oracle import geom
+    data = synthetic.make_cloud(a.points)
+    rid = geom.region_id(data[0], geom.fps(data, R)[0])
+    return data, rid, synthetic.make_orders(1000, R), synthetic.make_state_dict(a.model)
+
+
+def cpu_time_forwards(a, n_perm, batch_perms, repeats=1):
+    """Seconds per call of the oracle's shap_sampling_all_regions_batch on the host cores."""
+    import torch
+    from oracle import coalition, geom
+    geom.build()
+    data, rid, orders, sd = oracle_inputs(a)
+    t = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        coalition.shap_sampling_all_regions_batch(a.model, sd, data, LBL, rid, orders, R, batch_perms, n_perm)
+        t.append(time.perf_counter() - t0)
+    return t, torch.get_num_threads()
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU path.  The reference is pure Python/PyTorch and does not exist
+    on the GPU box, so this times its restatement oracle/ (kind "port") with all host threads; each step is
+    a bounded sample of the workload: 2 permutations x 33 clouds = 66 forwards."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    n_perm = 2
+    secs, cores = cpu_time_forwards(a, n_perm, 2, repeats=a.warmup + a.steps)
+    timed = secs[a.warmup:]
+    total = sum(timed)
+    fwd = n_perm * (R + 1) * len(timed)
+    value = fwd / total
+    sample = "%d steps x %d permutations x 33 clouds (%d forwards) of the same workload, oracle port, %d threads" % (
+        len(timed), n_perm, fwd, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(a, a.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def kernel_work(a):
+    """Algorithmic work per forward (one masked cloud) of every kernel family, for the roofline leg.
+    FLOPs are 2*MAC of the product the kernel evaluates; bytes are compulsory traffic."""
+    N, k = a.points, 20
+    w = {}
+    if a.model in ("dgcnn", "gcnn"):
+        w["sgemm_conv5_pool"] = ("tensor", 2.0 * N * 512 * 1024)
+        w["sgemm_edge_pq"] = ("tensor", 2.0 * N * (3 * 128 + 64 * 128 + 64 * 256 + 128 * 512))
+        if a.model == "dgcnn":
+            w["sgemm_gram"] = ("tensor", 2.0 * N * N * (64 + 64 + 128))
+            w["topk_rows"] = ("hbm", 3.0 * (4.0 * N * N + 4.0 * N * k))
+        w["gather_max"] = ("hbm", sum(4.0 * N * (2 * c + c) + 4.0 * N * k for c in (64, 64, 128, 256)))
+        w["knn_xyz"] = ("hbm", 12.0 * N + 4.0 * N * k)
+        w["sgemm_head"] = ("tensor", 2.0 * (2048 * 512 + 512 * 256 + 256 * 10))
+    else:
+        w["sgemm"] = ("tensor", 0.879e9)
+    w["mask_shapley"] = ("hbm", 12.0 * N)
+    w["reward"] = ("hbm", 44.0)
+    w["shapley_accumulate"] = ("hbm", 4.0 + 8.0 * R / (R + 1))
+    return w
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the iq_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from interpret_quality_b200 import _lib, build, ops, synthetic
+    from interpret_quality_b200.tools import final_common, final_util
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.load()
+
+    N = a.points
+    data_np = synthetic.make_cloud(N)
+    data_host = torch.from_numpy(data_np).pin_memory()
+    data_dev = data_host.to(dev)
+    fps_idx = ops.fps(data_dev, R)
+    rid_dev = ops.region_id(data_dev, fps_idx[0].contiguous())
+    rid_np = rid_dev.cpu().numpy()
+    all_orders = synthetic.make_orders(1000, R)
+    lo = (rank * a.perms) % 1000
+    if lo + a.perms > 1000:
+        lo = 0
+    orders_np = np.ascontiguousarray(all_orders[lo:lo + a.perms])
+    orders_dev = torch.from_numpy(orders_np).to(dev)
+    lbl = torch.tensor([LBL])
+    margs = types.SimpleNamespace(model=a.model, k=20, dataset="shapenet", feature_transform=True, device=dev,
+                                  num_points=N, num_regions=R, shapley_batch_size=5, num_samples=a.perms,
+                                  softmax_type="modified")
+    model = final_util.build_model(margs, synthetic.make_state_dict(a.model))
+    if a.chunk:
+        model.set_chunk(a.chunk)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    fwd_per_step = a.perms * (R + 1)
+
+    def resident_step():
+        with torch.no_grad():
+            phi_sum, _ = final_common.shapley_partial_sums(model, data_dev, lbl, rid_dev, orders_dev, margs)
+        if world > 1:
+            dist.all_reduce(phi_sum)
+        return phi_sum
+
+    def e2e_step():
+        # host buffers in, host result out: H2D of cloud / region ids / permutations and D2H of phi inside
+        return final_common.shap_sampling_all_regions_batch(model, data_host, lbl, rid_np, orders_np, margs)[0]
+
+    def timed(step_fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in ev:
+            flush.fill_(1)                                   # untimed L2 flush between timed steps
+            s.record()
+            step_fn()
+            e.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        total_ms = sum(s.elapsed_time(e) for s, e in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, clocks
+
+    # correctness gate before timing: phi of the first 4 permutations against the reference's golden vector
+    gate = None
+    gfile = os.path.join(ROOT, "tests", "golden", "%s.npz" % a.model)
+    if rank == 0 and N == 1024 and os.path.exists(gfile):
+        g = np.load(gfile)
+        ga = types.SimpleNamespace(**vars(margs))
+        ga.shapley_batch_size, ga.num_samples = 2, int(g["shapley_nperm"])
+        grid = np.load(os.path.join(ROOT, "tests", "golden", "geometry.npz"))["region_id_1024"]
+        assert np.array_equal(grid, rid_np), "region ids differ from the reference's golden vector"
+        phi, lg = final_common.shap_sampling_all_regions_batch(model, data_host, lbl, rid_np, all_orders, ga)
+        e_phi = float(np.abs(phi - g["shapley_phi"]).max() / np.abs(g["shapley_phi"]).max())
+        e_lg = float(np.abs(lg.cpu().numpy() - g["shapley_logits"]).max() / np.abs(g["shapley_logits"]).max())
+        gate = {"phi_rel_err": e_phi, "logits_rel_err": e_lg, "tolerance": 1e-3}
+        if not (e_phi <= 1e-3 and e_lg <= 1e-3):
+            raise RuntimeError("parity gate failed: %s" % gate)
+
+    total_ms, launches, clocks = timed(resident_step, a.steps, max(a.warmup, 3), ClockSampler(local))
+    value = world * fwd_per_step * a.steps / (total_ms * 1e-3)
+    e2e_ms, _, _ = timed(e2e_step, a.steps, 1)
+    e2e_value = world * fwd_per_step * a.steps / (e2e_ms * 1e-3)
+    h2d = int(data_host.numel() * 4 + orders_np.nbytes + rid_np.nbytes)
+    d2h = int(R * 8)
+
+    # per-kernel timing of one more step (CUDA events around every launch, on the launching stream)
+    roofline, breakdown = None, None
+    if rank == 0:
+        _lib.profile_enable(True)
+        resident_step()
+        rep = _lib.profile_report()
+        _lib.profile_enable(False)
+        pk = peaks()
+        work = kernel_work(a)
+        tot = sum(ms for ms, _ in rep.values())
+        breakdown = {k: {"ms": round(ms, 3), "launches": n, "share": round(ms / tot, 4)} for k, (ms, n) in
+                     sorted(rep.items(), key=lambda kv: -kv[1][0])}
+        for name, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+            if name not in work:
+                continue
+            bound, per_fwd = work[name]
+            per_launch = per_fwd * fwd_per_step / n
+            dur = ms * 1e-3 / n
+            if bound == "tensor":
+                ach, peak, unit = per_launch / dur / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
+            else:
+                ach, peak, unit = per_launch / dur / 1e9, pk["hbm_gbs"], "GB/s"
+            roofline = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "traffic": None, "avg_launch_ms": dur * 1e3, "launches_per_step": n,
+                        "algorithmic_per_launch": per_launch, "peak_source": pk["source"],
+                        "note": "peak = measured dense bf16 (sustained) / copy bandwidth of MEASURED_PEAKS.json; "
+                                "the kernel computes in fp32"}
+            break
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        n_perm = 4
+        secs, cores = cpu_time_forwards(a, n_perm, 2)
+        cpu = {"value": n_perm * (R + 1) / secs[0], "unit": UNIT, "cores": cores, "kind": "port",
+               "host_cpus": os.cpu_count(),
+               "sample": "%d permutations x 33 clouds (%d forwards) of the same workload, oracle port of the "
+                         "reference's torch-CPU path, %d threads" % (n_perm, n_perm * (R + 1), cores)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_of(a, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / a.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_gate": gate,
+                "breakdown": breakdown,
+                "as_written_tflops": (value * MODEL_GFLOP[a.model] / 1e3) if a.points == 1024 else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,145 @@
+/*
+ * iq_b200 -- C ABI of the B200-native coalition-evaluation path of
+ * ada-shen/Interpret_quality (FPS regions -> coalition masking -> masked forward
+ * -> Shapley / interaction reduction).
+ *
+ * Conventions
+ *   - every pointer named *_dev is device memory on the current CUDA device,
+ *     owned by the caller (torch's caching allocator in the Python host);
+ *     nothing here allocates on the forward path except iq_model_create;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); every
+ *     call only enqueues work on it, there are no hidden synchronisations;
+ *   - tensors are dense, row-major, float32 / int64 exactly like the reference's
+ *     torch tensors and numpy arrays;
+ *   - return value 0 = ok, negative = error, message via iq_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Each entry names the reference function (file:line in ada-shen/Interpret_quality)
+ * whose behaviour it reproduces.  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef IQ_B200_H
+#define IQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct iq_model iq_model;
+
+/* library state */
+int iq_version(void);
+const char *iq_last_error(void);
+/* number of CUDA kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t iq_launch_count(void);
+
+/* Per-kernel timing for bench.py's roofline leg: while enabled, every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  iq_profile_report synchronises the device and returns the
+ * number of distinct kernel names, filling up to `cap` (name, total milliseconds, launches) triples. */
+int iq_profile_enable(int on);
+int iq_profile_report(const char **names, double *ms, long long *counts, int cap);
+
+/* ---- regions ------------------------------------------------------------------------- */
+
+/* farthest_point_sample(xyz, npoint): final_save_fps.py:10-31 (same loop in
+ * models/pointnet2.py:45-68, models/pointconv.py:54-77).
+ * xyz (B,N,3) f32 -> idx (B,npoint) i64; start index 0, lowest index on ties. */
+int iq_fps(const float *xyz_dev, int64_t B, int64_t N, int64_t npoint, int64_t *idx_dev, void *stream);
+
+/* square_distance(src, dst) for 3-d points: tools/final_util.py:134-147.
+ * src (B,N,3), dst (B,M,3) -> out (B,N,M) f32. */
+int iq_square_distance3(const float *src_dev, const float *dst_dev, int64_t B, int64_t N, int64_t M, float *out_dev,
+                        void *stream);
+
+/* cal_region_id(data, fps_index): final_shapley_value.py:20-35.
+ * xyz (N,3) f32, fps_index (R) i64 -> region_id (N) i64 (argmin, first minimum). */
+int iq_region_id(const float *xyz_dev, const int64_t *fps_index_dev, int64_t N, int64_t R, int64_t *region_id_dev,
+                 void *stream);
+
+/* torch.mean(data, dim=1).squeeze(): tools/final_common.py:80.  xyz (N,3) -> center (3). */
+int iq_center(const float *xyz_dev, int64_t N, float *center_dev, void *stream);
+
+/* ---- coalition masking --------------------------------------------------------------- */
+
+/* mask_data_batch(masked_data, center, orders, region_id, args): tools/final_common.py:46-61
+ * (single permutation: mask_data, final_shapley_value.py:74-88).
+ * in_place = 1: masked_dev ((R+1)*bs, N, 3) already holds bs*(R+1) copies of the cloud and only the
+ *               masked entries are overwritten (the reference's mutate-and-return contract);
+ *               data_dev may be NULL.
+ * in_place = 0: the expansion data.expand(...).clone() of tools/final_common.py:88 is fused in and
+ *               every element of masked_dev is written from data_dev (N,3). */
+int iq_mask_shapley(const float *data_dev, const float *center_dev, const int64_t *orders_dev,
+                    const int64_t *region_id_dev, int64_t bs, int64_t R, int64_t N, float *masked_dev, int in_place,
+                    void *stream);
+
+/* the 4-clouds-per-context block of compute_order_interaction_logits:
+ * final_point_binary_interaction_logits.py:42-56.  data (N,3), contexts (ctx,m) i64 ->
+ * out (4*ctx, 3, N) channel-first (point_major = 0, the reference layout) or (4*ctx, N, 3). */
+int iq_mask_interaction(const float *data_dev, const float *center_dev, const int64_t *contexts_dev, int64_t ctx,
+                        int64_t m, int64_t region_i, int64_t region_j, const int64_t *region_id_dev, int64_t R,
+                        int64_t N, int point_major, float *out_dev, void *stream);
+
+/* ---- reward and reductions ----------------------------------------------------------- */
+
+/* get_reward(logits, lbl, args): tools/final_common.py:11-24.
+ * softmax_normal = 1 -> "normal" (log_softmax[:, lbl]); 0 -> "modified" (and any other string). */
+int iq_reward(const float *logits_dev, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v_dev,
+              void *stream);
+
+/* the per-permutation loop of shap_sampling_all_regions_batch: tools/final_common.py:93-96.
+ * phi_sum[orders[p][r]] += (double)(v[p][r+1] - v[p][r]) for p = 0..bs-1 in order; the caller divides by
+ * num_samples (tools/final_common.py:97).  v ((R+1)*bs) f32, orders (bs,R) i64, phi_sum (R) f64. */
+int iq_shapley_accumulate(const float *v_dev, const int64_t *orders_dev, int64_t bs, int64_t R, double *phi_sum_dev,
+                          void *stream);
+
+/* compute_order_interaction(all_logits, lbl, args): final_cal_interactions.py:14-37.
+ * logits (P, 4*ctx, C) f32 -> out (P, ctx) f64 = v[4k] + v[4k+3] - v[4k+1] - v[4k+2]. */
+int iq_interaction_reduce(const float *logits_dev, int64_t P, int64_t ctx, int64_t C, int64_t lbl, int softmax_normal,
+                          double *out_dev, void *stream);
+
+/* ---- masked forward ------------------------------------------------------------------ */
+
+/* load_model(args): tools/final_util.py:236-262.  kind in {"pointnet","pointnet2","pointconv","dgcnn","gcnn"}
+ * selects PointNetCls / PointNet2ClsMsg / PointConvDensityClsSsg / DGCNN_cls / GCNN_cls (models/*.py).
+ * The weights arrive as the checkpoint's state dict: n_tensors float32 host arrays with the
+ * reference's key names ("module." prefix already stripped).  k = args.k (DGCNN/GCNN).
+ * Returns NULL on error. */
+iq_model *iq_model_create(const char *kind, int n_tensors, const char *const *names, const float *const *host_data,
+                          const int64_t *numel, int k, int num_classes);
+void iq_model_destroy(iq_model *m);
+
+/* clouds processed per internal pass (tuning knob; results do not depend on it) */
+int iq_model_set_chunk(iq_model *m, int chunk);
+int iq_model_get_chunk(const iq_model *m);
+
+/* bytes of scratch iq_model_forward needs for B clouds of N points */
+int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N);
+
+/* model(data) in eval mode under no_grad: the forward of models/*.py.
+ * x_dev: (B,3,N) when point_major = 0 (the nn.Module contract) or (B,N,3) when 1.
+ * logits_dev (B, num_classes).  PointNet only (may be NULL): trans_feat_dev (B,64,64),
+ * crt_points_dev (B,1024) i64 -- the other two members of PointNetCls.forward's tuple. */
+int iq_model_forward(iq_model *m, const float *x_dev, int point_major, int64_t B, int64_t N, float *logits_dev,
+                     void *workspace_dev, int64_t workspace_bytes, float *trans_feat_dev, int64_t *crt_points_dev,
+                     void *stream);
+
+/* ---- building blocks of the forward pass, exported for unit tests ---------------------------- */
+
+/* knn(x, k) for 3-d input: models/dgcnn.py:12-18.  xyz (B,N,3) point-major -> idx (B,N,k) i32, the k
+ * largest of -|xj|^2 + 2 xi.xj - |xi|^2 per row, unordered, lowest index on ties at the boundary. */
+int iq_knn_xyz(const float *xyz_dev, int64_t B, int64_t N, int k, int32_t *idx_dev, void *stream);
+
+/* torch.topk(keys, k, dim=-1, largest, sorted=False)[1] on a (rows, N) matrix with row stride ld. */
+int iq_topk_rows(const float *keys_dev, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx_dev,
+                 void *stream);
+
+/* y = act(x W^T + b): x (M,K), W (N,K), b (N) or NULL, act 0 none / 1 relu / 2 leaky_relu(0.2).
+ * engine 0 = exact fp32 SIMT GEMM, 1 = tcgen05 3xTF32 GEMM (when built in). */
+int iq_linear(const float *x_dev, const float *w_dev, const float *b_dev, int64_t M, int64_t N, int64_t K, int act,
+              int engine, float *y_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQ_B200_H */

@@ -1,0 +1,172 @@
+// extern "C" surface of libiq_b200 (declared in include/iq_b200.h).
+#include <string.h>
+
+#include "../../include/iq_b200.h"
+#include "model.cuh"
+
+using namespace iq;
+
+struct iq_model {
+    std::unique_ptr<Model> impl;
+};
+
+extern "C" {
+
+int iq_version(void) { return 100; }
+const char *iq_last_error(void) { return last_error(); }
+uint64_t iq_launch_count(void) { return g_launch_count; }
+
+int iq_profile_enable(int on)
+{
+    profile_enable(on != 0);
+    return 0;
+}
+
+int iq_profile_report(const char **names, double *ms, long long *counts, int cap)
+{
+    return profile_report(names, ms, counts, cap);
+}
+
+int iq_fps(const float *xyz, int64_t B, int64_t N, int64_t npoint, int64_t *idx, void *stream)
+{
+    IQ_CHECK(xyz && idx, "iq_fps: null pointer");
+    return launch_fps(xyz, B, N, npoint, idx, nullptr, nullptr, as_stream(stream));
+}
+
+int iq_square_distance3(const float *src, const float *dst, int64_t B, int64_t N, int64_t M, float *out, void *stream)
+{
+    IQ_CHECK(src && dst && out, "iq_square_distance3: null pointer");
+    return launch_square_distance3(src, dst, B, N, M, out, as_stream(stream));
+}
+
+int iq_region_id(const float *xyz, const int64_t *fps_index, int64_t N, int64_t R, int64_t *region_id, void *stream)
+{
+    IQ_CHECK(xyz && fps_index && region_id, "iq_region_id: null pointer");
+    return launch_region_id(xyz, fps_index, N, R, region_id, as_stream(stream));
+}
+
+int iq_center(const float *xyz, int64_t N, float *center, void *stream)
+{
+    IQ_CHECK(xyz && center, "iq_center: null pointer");
+    return launch_center(xyz, N, center, as_stream(stream));
+}
+
+int iq_mask_shapley(const float *data, const float *center, const int64_t *orders, const int64_t *region_id, int64_t bs,
+                    int64_t R, int64_t N, float *masked, int in_place, void *stream)
+{
+    IQ_CHECK(center && orders && region_id && masked, "iq_mask_shapley: null pointer");
+    IQ_CHECK(in_place || data, "iq_mask_shapley: data is required unless in_place");
+    return launch_mask_shapley(data, center, orders, region_id, bs, R, N, masked, in_place != 0, as_stream(stream));
+}
+
+int iq_mask_interaction(const float *data, const float *center, const int64_t *contexts, int64_t ctx, int64_t m,
+                        int64_t region_i, int64_t region_j, const int64_t *region_id, int64_t R, int64_t N,
+                        int point_major, float *out, void *stream)
+{
+    IQ_CHECK(data && center && region_id && out, "iq_mask_interaction: null pointer");
+    IQ_CHECK(contexts || m == 0 || ctx == 0, "iq_mask_interaction: null contexts");
+    return launch_mask_interaction(data, center, contexts, ctx, m, region_i, region_j, region_id, R, N, point_major, out,
+                                   as_stream(stream));
+}
+
+int iq_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v, void *stream)
+{
+    IQ_CHECK(logits && v, "iq_reward: null pointer");
+    return launch_reward(logits, B, C, lbl, softmax_normal, v, as_stream(stream));
+}
+
+int iq_shapley_accumulate(const float *v, const int64_t *orders, int64_t bs, int64_t R, double *phi_sum, void *stream)
+{
+    IQ_CHECK(v && orders && phi_sum, "iq_shapley_accumulate: null pointer");
+    return launch_shapley_accumulate(v, orders, bs, R, phi_sum, as_stream(stream));
+}
+
+int iq_interaction_reduce(const float *logits, int64_t P, int64_t ctx, int64_t C, int64_t lbl, int softmax_normal,
+                          double *out, void *stream)
+{
+    IQ_CHECK(logits && out, "iq_interaction_reduce: null pointer");
+    return launch_interaction_reduce(logits, P, ctx, C, lbl, softmax_normal, out, as_stream(stream));
+}
+
+iq_model *iq_model_create(const char *kind, int n_tensors, const char *const *names, const float *const *host_data,
+                          const int64_t *numel, int k, int num_classes)
+{
+    if (!kind || (n_tensors > 0 && (!names || !host_data || !numel))) {
+        set_error("iq_model_create: null argument");
+        return nullptr;
+    }
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        set_error("iq_model_create: no CUDA device (this library has no CPU fallback)");
+        return nullptr;
+    }
+    StateDict sd;
+    for (int i = 0; i < n_tensors; ++i) {
+        std::string key = names[i];
+        if (key.compare(0, 7, "module.") == 0) key = key.substr(7);   // tools/final_util.py:253-257
+        sd[key] = HostTensor{host_data[i], numel[i]};
+    }
+    std::string err;
+    Model *impl = nullptr;
+    const std::string kd = kind;
+    if (kd == "dgcnn") impl = create_edgeconv_model(sd, true, k, num_classes, err);
+    else if (kd == "gcnn" || kd == "gcnn_adv") impl = create_edgeconv_model(sd, false, k, num_classes, err);
+    else if (kd == "pointnet") impl = create_pointnet_model(sd, num_classes, err);
+    else err = "unknown model kind '" + kd + "'";
+    if (!impl) {
+        set_error("iq_model_create: " + err);
+        return nullptr;
+    }
+    iq_model *m = new iq_model();
+    m->impl.reset(impl);
+    return m;
+}
+
+void iq_model_destroy(iq_model *m) { delete m; }
+
+int iq_model_set_chunk(iq_model *m, int chunk)
+{
+    IQ_CHECK(m && chunk >= 1, "iq_model_set_chunk: bad argument");
+    m->impl->chunk = chunk;
+    return 0;
+}
+
+int iq_model_get_chunk(const iq_model *m) { return m ? m->impl->chunk : -1; }
+
+int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N)
+{
+    if (!m) { set_error("iq_model_workspace_bytes: null model"); return -1; }
+    return m->impl->workspace_bytes(B, N);
+}
+
+int iq_model_forward(iq_model *m, const float *x, int point_major, int64_t B, int64_t N, float *logits, void *ws,
+                     int64_t ws_bytes, float *trans_feat, int64_t *crt_points, void *stream)
+{
+    IQ_CHECK(m, "iq_model_forward: null model");
+    return m->impl->forward(x, point_major, B, N, logits, ws, ws_bytes, trans_feat, crt_points, as_stream(stream));
+}
+
+int iq_knn_xyz(const float *xyz, int64_t B, int64_t N, int k, int32_t *idx, void *stream)
+{
+    IQ_CHECK(xyz && idx, "iq_knn_xyz: null pointer");
+    return launch_knn_xyz(xyz, 1, B, N, k, idx, as_stream(stream));
+}
+
+int iq_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx, void *stream)
+{
+    IQ_CHECK(keys && idx, "iq_topk_rows: null pointer");
+    return launch_topk_rows(keys, rows, N, ld, k, largest, idx, as_stream(stream));
+}
+
+int iq_linear(const float *x, const float *w, const float *b, int64_t M, int64_t N, int64_t K, int act, int engine,
+              float *y, void *stream)
+{
+    IQ_CHECK(x && w && y, "iq_linear: null pointer");
+    IQ_CHECK(engine == 0, "iq_linear: only the fp32 SIMT engine is built in");
+    GemmDesc g;
+    g.A = x; g.lda = K; g.B = w; g.ldb = K; g.C = y; g.ldc = N;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bias = b; g.act = act;
+    return launch_sgemm(g, as_stream(stream));
+}
+
+}  // extern "C"

@@ -84,6 +84,7 @@ mask_shapley_kernel(const float *__restrict__ data, const float *__restrict__ ce
 int launch_mask_shapley(const float *data, const float *center, const int64_t *orders, const int64_t *region_id,
                         int64_t bs, int64_t R, int64_t N, float *out, bool in_place, cudaStream_t st)
 {
+    ProfileScope _ps("mask_shapley", st);
     IQ_CHECK(R >= 1 && R <= 255, "mask_shapley: num_regions must be in [1,255]");
     IQ_CHECK(N >= 4 && (3 * N) % 4 == 0, "mask_shapley: num_points must be a multiple of 4");
     IQ_CHECK(N <= 48 * 1024, "mask_shapley: num_points too large for the shared-memory lookup");
@@ -147,6 +148,7 @@ int launch_mask_interaction(const float *data, const float *center, const int64_
                             int64_t region_i, int64_t region_j, const int64_t *region_id, int64_t R, int64_t N,
                             int point_major, float *out, cudaStream_t st)
 {
+    ProfileScope _ps("mask_interaction", st);
     IQ_CHECK(R >= 1 && R <= 255, "mask_interaction: num_regions must be in [1,255]");
     if (ctx == 0) return 0;
     mask_interaction_kernel<<<(unsigned)ctx, 256, 0, st>>>(data, center, contexts, (int)m, (int)region_i, (int)region_j,
@@ -179,6 +181,7 @@ __global__ void reward_kernel(const float *__restrict__ logits, int64_t B, int C
 
 int launch_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v, cudaStream_t st)
 {
+    ProfileScope _ps("reward", st);
     IQ_CHECK(C >= 2 && lbl >= 0 && lbl < C, "reward: label out of range");
     if (B == 0) return 0;
     reward_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(logits, B, (int)C, (int)lbl, softmax_normal, v);
@@ -220,6 +223,7 @@ shapley_accumulate_kernel(const float *__restrict__ v, const int64_t *__restrict
 int launch_shapley_accumulate(const float *v, const int64_t *orders, int64_t bs, int64_t R, double *phi_sum,
                               cudaStream_t st)
 {
+    ProfileScope _ps("shapley_accumulate", st);
     IQ_CHECK(R >= 1 && R <= 255, "shapley_accumulate: num_regions must be in [1,255]");
     if (bs == 0) return 0;
     const int threads = (int)((1024 / R) * R);
@@ -249,6 +253,7 @@ __global__ void interaction_reduce_kernel(const float *__restrict__ logits, int6
 int launch_interaction_reduce(const float *logits, int64_t P, int64_t ctx, int64_t C, int64_t lbl, int softmax_normal,
                               double *out, cudaStream_t st)
 {
+    ProfileScope _ps("interaction_reduce", st);
     IQ_CHECK(C >= 2 && lbl >= 0 && lbl < C, "interaction_reduce: label out of range");
     const int64_t total = P * ctx;
     if (total == 0) return 0;

@@ -41,6 +41,17 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 extern unsigned long long g_launch_count;
 #define IQ_COUNT_LAUNCH() (++::iq::g_launch_count)
 
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
+struct ProfileScope {
+    ProfileScope(const char *name, cudaStream_t st);
+    ~ProfileScope();
+    int slot;
+    cudaStream_t st;
+};
+void profile_enable(bool on);
+// synchronises, then fills up to `cap` entries; returns the number of distinct kernel names
+int profile_report(const char **names, double *ms, long long *counts, int cap);
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
 
 __device__ __forceinline__ float apply_act(float v, int act)

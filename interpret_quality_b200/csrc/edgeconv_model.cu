@@ -1,0 +1,145 @@
+// DGCNN_cls / GCNN_cls forward pass (eval mode) on the folded weights.
+//
+// Reference behaviour restated (never copied): models/dgcnn.py:51-120 (dynamic
+// graph recomputed in feature space before every EdgeConv) and :123-194 (graph
+// fixed on the input coordinates).  State-dict keys are the reference's
+// checkpoint names (conv%d.0.weight, bn%d.*, conv5.0.weight, linear%d.*).
+//
+// Per chunk of clouds (activations are point-major, (cloud*N + point, channel)):
+//   layer l:  idx  = top-k of 2 X X^T - |x_j|^2         (knn_xyz / batched GEMM + topk_rows)
+//             PQ   = X [s*Wa ; s*(Wb-Wa)]^T + [0 ; t]    (GEMM)
+//             X_l  = lrelu(max_j P[idx] + Q)             (gather_max) -> column slice of the 512-wide concat
+//   conv5 + BN + lrelu with fused max / mean pooling over the points, then the 3-layer head.
+#include "model.cuh"
+
+namespace iq {
+
+namespace {
+
+struct EdgeLayer {
+    float *wcat = nullptr;       // (2*cout, cin): rows [0,cout) = s*Wa, rows [cout,2cout) = s*(Wb - Wa)
+    float *bcat = nullptr;       // (2*cout): [0 ; t]
+    int cin = 0, cout = 0, col = 0;
+};
+
+class EdgeConvModel : public Model {
+public:
+    bool dynamic = true;
+    int k = 20;
+    EdgeLayer layers[4];
+    Dense conv5, lin1, lin2, lin3;
+    const char *kind() const override { return dynamic ? "dgcnn" : "gcnn"; }
+
+protected:
+    int plan_and_run(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *logits, float *,
+                     int64_t *, cudaStream_t st) override
+    {
+        IQ_CHECK(N % 128 == 0, "dgcnn/gcnn: num_points must be a multiple of 128");
+        IQ_CHECK(N <= 2048, "dgcnn/gcnn: num_points must be <= 2048");
+        IQ_CHECK(k <= N, "dgcnn/gcnn: k exceeds num_points");
+        const int64_t rows = Bc * N;
+        float *xyz = ws.take<float>(rows * 3);
+        int32_t *idx = ws.take<int32_t>(rows * k);
+        float *feat = ws.take<float>(rows * 512);
+        float *nxx = ws.take<float>(rows);
+        float *pq = ws.take<float>(rows * 512);
+        float *dist = dynamic ? ws.take<float>(Bc * N * N) : nullptr;
+        const int tiles = (int)(N / 128);
+        float *pmax = ws.take<float>(Bc * tiles * 1024);
+        float *psum = ws.take<float>(Bc * tiles * 1024);
+        float *g = ws.take<float>(Bc * 2048);
+        float *h1 = ws.take<float>(Bc * 512);
+        float *h2 = ws.take<float>(Bc * 256);
+        IQ_CHECK(ws.ok(), "dgcnn/gcnn: workspace too small");
+        if (ws.dry) return 0;
+
+        const float *pts = x;
+        if (!point_major) {
+            if (int rc = launch_xyz_to_point_major(x, Bc, N, xyz, st)) return rc;
+            pts = xyz;
+        }
+        if (int rc = launch_knn_xyz(pts, 1, Bc, N, k, idx, st)) return rc;
+        for (int l = 0; l < 4; ++l) {
+            const EdgeLayer &L = layers[l];
+            const float *in = l == 0 ? pts : feat + layers[l - 1].col;
+            const int64_t ldin = l == 0 ? 3 : 512;
+            if (l > 0 && dynamic) {
+                GemmDesc d;
+                d.A = in; d.lda = ldin; d.strideA = N * ldin;
+                d.B = in; d.ldb = ldin; d.strideB = N * ldin;
+                d.C = dist; d.ldc = N; d.strideC = N * N;
+                d.M = (int)N; d.N = (int)N; d.K = L.cin; d.batch = (int)Bc;
+                d.alpha = 2.0f; d.bias = nxx; d.strideBias = N; d.tag = "sgemm_gram";
+                if (int rc = launch_sgemm(d, st)) return rc;
+                if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
+            }
+            GemmDesc p;
+            p.A = in; p.lda = ldin; p.B = L.wcat; p.ldb = L.cin; p.C = pq; p.ldc = 2 * L.cout;
+            p.M = (int)rows; p.N = 2 * L.cout; p.K = L.cin; p.bias = L.bcat; p.tag = "sgemm_edge_pq";
+            if (int rc = launch_sgemm(p, st)) return rc;
+            if (int rc = launch_gather_max(pq, 2 * L.cout, idx, Bc, N, k, L.cout, ACT_LRELU, feat + L.col, 512,
+                                           (dynamic && l < 3) ? nxx : nullptr, st))
+                return rc;
+        }
+        GemmDesc c5;
+        c5.A = feat; c5.lda = 512; c5.B = conv5.w; c5.ldb = 512; c5.M = (int)rows; c5.N = 1024; c5.K = 512;
+        c5.bias = conv5.b; c5.act = ACT_LRELU; c5.pool_max = pmax; c5.pool_sum = psum; c5.tag = "sgemm_conv5_pool";
+        if (int rc = launch_sgemm(c5, st)) return rc;
+        if (int rc = launch_pool_finish(pmax, nullptr, psum, Bc, tiles, (int)N, 1024, g, 2048, nullptr, g + 1024, 2048, st))
+            return rc;
+        const Dense *head[3] = {&lin1, &lin2, &lin3};
+        const float *hin[3] = {g, h1, h2};
+        float *hout[3] = {h1, h2, logits};
+        for (int i = 0; i < 3; ++i) {
+            GemmDesc h;
+            h.A = hin[i]; h.lda = head[i]->cin; h.B = head[i]->w; h.ldb = head[i]->cin;
+            h.C = hout[i]; h.ldc = head[i]->cout; h.M = (int)Bc; h.N = head[i]->cout; h.K = head[i]->cin;
+            h.bias = head[i]->b; h.act = i < 2 ? ACT_LRELU : ACT_NONE; h.tag = "sgemm_head";
+            if (int rc = launch_sgemm(h, st)) return rc;
+        }
+        return 0;
+    }
+};
+
+}  // namespace
+
+Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int num_classes, std::string &err)
+{
+    std::unique_ptr<EdgeConvModel> m(new EdgeConvModel());
+    m->dynamic = dynamic_graph;
+    m->k = k;
+    m->num_classes = num_classes;
+    m->chunk = 32;
+    const int cin[4] = {3, 64, 64, 128}, cout[4] = {64, 64, 128, 256}, col[4] = {0, 64, 128, 256};
+    for (int l = 0; l < 4; ++l) {
+        std::vector<float> w, b;
+        const std::string n = std::to_string(l + 1);
+        if (!fold_dense(sd, "conv" + n + ".0.weight", "", "bn" + n, cout[l], 2 * cin[l], w, b, err)) return nullptr;
+        // W = [Wa | Wb] over the 2*cin input channels [x_j - x_i ; x_i]
+        std::vector<float> wcat((size_t)2 * cout[l] * cin[l]), bcat((size_t)2 * cout[l], 0.0f);
+        for (int o = 0; o < cout[l]; ++o)
+            for (int i = 0; i < cin[l]; ++i) {
+                const float wa = w[(size_t)o * 2 * cin[l] + i], wb = w[(size_t)o * 2 * cin[l] + cin[l] + i];
+                wcat[(size_t)o * cin[l] + i] = wa;
+                wcat[(size_t)(cout[l] + o) * cin[l] + i] = (float)((double)wb - (double)wa);
+            }
+        for (int o = 0; o < cout[l]; ++o) bcat[cout[l] + o] = b[o];
+        EdgeLayer &L = m->layers[l];
+        L.cin = cin[l]; L.cout = cout[l]; L.col = col[l];
+        if (m->arena_.upload(wcat, &L.wcat) || m->arena_.upload(bcat, &L.bcat)) { err = last_error(); return nullptr; }
+    }
+    struct { Dense *d; const char *w; const char *b; const char *bn; int co, ci; } dense[4] = {
+        {&m->conv5, "conv5.0.weight", "", "bn5", 1024, 512},
+        {&m->lin1, "linear1.weight", "", "bn6", 512, 2048},
+        {&m->lin2, "linear2.weight", "linear2.bias", "bn7", 256, 512},
+        {&m->lin3, "linear3.weight", "linear3.bias", "", num_classes, 256}};
+    for (auto &e : dense) {
+        std::vector<float> w, b;
+        if (!fold_dense(sd, e.w, e.b, e.bn, e.co, e.ci, w, b, err)) return nullptr;
+        e.d->cout = e.co; e.d->cin = e.ci;
+        if (m->arena_.upload(w, &e.d->w) || m->arena_.upload(b, &e.d->b)) { err = last_error(); return nullptr; }
+    }
+    return m.release();
+}
+
+}  // namespace iq

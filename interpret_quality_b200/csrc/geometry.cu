@@ -83,6 +83,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, int64_t *__restrict
 int launch_fps(const float *xyz, int64_t B, int64_t N, int64_t npoint, int64_t *idx64, int32_t *idx32, float *new_xyz,
                cudaStream_t st)
 {
+    ProfileScope _ps("fps", st);
     IQ_CHECK(N >= 1 && N <= 4096, "fps: num_points must be in [1,4096]");
     IQ_CHECK(npoint >= 1, "fps: npoint must be positive");
     if (B == 0) return 0;
@@ -128,6 +129,7 @@ __global__ void square_distance3_kernel(const float *__restrict__ src, const flo
 int launch_square_distance3(const float *src, const float *dst, int64_t B, int64_t N, int64_t M, float *out,
                             cudaStream_t st)
 {
+    ProfileScope _ps("square_distance3", st);
     if (B * N * M == 0) return 0;
     IQ_CHECK(N <= 65535 && B <= 65535, "square_distance3: N and B must be <= 65535");
     dim3 grid((unsigned)ceil_div(M, 128), (unsigned)N, (unsigned)B);
@@ -164,6 +166,7 @@ __global__ void region_id_kernel(const float *__restrict__ xyz, const int64_t *_
 int launch_region_id(const float *xyz, const int64_t *fps_index, int64_t N, int64_t R, int64_t *region_id,
                      cudaStream_t st)
 {
+    ProfileScope _ps("region_id", st);
     IQ_CHECK(R >= 1 && R <= 2048, "region_id: num_regions out of range");
     if (N == 0) return 0;
     region_id_kernel<<<(unsigned)ceil_div(N, 128), 128, sizeof(float) * 4 * (size_t)R, st>>>(xyz, fps_index, (int)N,
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(256) center_kernel(const float *__restrict__ x
 
 int launch_center(const float *xyz, int64_t N, float *center, cudaStream_t st)
 {
+    ProfileScope _ps("center", st);
     IQ_CHECK(N >= 1, "center: empty cloud");
     center_kernel<<<1, 256, 0, st>>>(xyz, (int)N, center);
     IQ_COUNT_LAUNCH();

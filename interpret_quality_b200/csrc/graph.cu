@@ -1,0 +1,349 @@
+// kNN graph construction and EdgeConv aggregation for DGCNN / GCNN.
+//
+// Reference behaviour restated (never copied):
+//   knn                 models/dgcnn.py:12-18   top-k of  -|xj|^2 + 2 xi.xj - |xi|^2
+//   get_graph_feature   models/dgcnn.py:21-47   [x_j - x_i ; x_i] per edge
+//   conv + BN + LeakyReLU + max over k   models/dgcnn.py:92-105
+//
+// B200-first restructuring (DESIGN.md section "EdgeConv"): because the 1x1 conv is
+// linear and LeakyReLU is monotone,
+//     max_j lrelu(s*(Wa (x_j - x_i) + Wb x_i) + t) = lrelu(max_j P_j + Q_i),
+//     P = (s*Wa) x,  Q = (s*(Wb - Wa)) x + t,
+// so the (B, 2C, N, k) edge tensor is never materialised: one dense per-point GEMM
+// (sgemm.cu / gemm_tc.cu) followed by the gather-max kernel below.
+//
+// Top-k is exact: the k-th largest key of a row is found per warp (lane maxima ->
+// lower bound -> compaction of the few keys above it in shared memory -> rank
+// select; bitwise radix descent as the general fallback) and ties at the boundary
+// are broken by lowest index.  Masked clouds collapse hundreds of points onto one
+// coordinate, so huge tie groups are the common case, not the corner case.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace iq {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TOPK_SCRATCH = 64;
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// k largest of the 32*V keys of a warp; lane l holds candidates j = v*32 + l.
+// Writes k candidate indices (unordered) to out[0..k).  scratch: TOPK_SCRATCH floats per warp.
+template <int V>
+__device__ __forceinline__ void warp_topk(const float (&key)[V], int k, int lane, int32_t *out, float *scratch)
+{
+    float T = 0.0f;
+    bool have = false;
+    if (k <= 32) {
+        float m = key[0];
+#pragma unroll
+        for (int v = 1; v < V; ++v) m = fmaxf(m, key[v]);
+        int r = 0;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const float o = __shfl_sync(FULL, m, s);
+            r += (o > m || (o == m && s < lane)) ? 1 : 0;
+        }
+        const unsigned bal = __ballot_sync(FULL, r == k - 1);
+        const float T0 = __shfl_sync(FULL, m, __ffs(bal) - 1);     // >= k keys are >= T0
+        int g = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) g += key[v] > T0 ? 1 : 0;
+        const int G = __reduce_add_sync(FULL, g);
+        if (G < k) {
+            T = T0;
+            have = true;
+        } else if (G <= TOPK_SCRATCH) {
+            int base = 0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const bool pred = key[v] > T0;
+                const unsigned b = __ballot_sync(FULL, pred);
+                if (pred) scratch[base + __popc(b & lanemask_lt())] = key[v];
+                base += __popc(b);
+            }
+            __syncwarp();
+            const float c0 = lane < G ? scratch[lane] : -INFINITY;
+            const float c1 = lane + 32 < G ? scratch[lane + 32] : -INFINITY;
+            int gt0 = 0, ge0 = 0, gt1 = 0, ge1 = 0;
+            for (int t = 0; t < G; ++t) {
+                const float x = scratch[t];
+                gt0 += x > c0; ge0 += x >= c0; gt1 += x > c1; ge1 += x >= c1;
+            }
+            const bool hit0 = lane < G && gt0 < k && ge0 >= k;
+            const bool hit1 = lane + 32 < G && gt1 < k && ge1 >= k;
+            const unsigned b0 = __ballot_sync(FULL, hit0), b1 = __ballot_sync(FULL, hit1);
+            const float t0 = __shfl_sync(FULL, c0, b0 ? __ffs(b0) - 1 : 0);
+            const float t1 = __shfl_sync(FULL, c1, b1 ? __ffs(b1) - 1 : 0);
+            T = b0 ? t0 : t1;
+            have = true;
+            __syncwarp();
+        }
+    }
+    if (!have) {                                                   // exact radix descent on the ordered bit pattern
+        uint32_t tu = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = tu | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) c += ordered_u32(key[v]) >= cand ? 1 : 0;
+            if (__reduce_add_sync(FULL, c) >= k) tu = cand;
+        }
+        T = from_ordered_u32(tu);
+    }
+    int g2 = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) g2 += key[v] > T ? 1 : 0;
+    const int G2 = __reduce_add_sync(FULL, g2);
+    const int need = k - G2;
+    int base_gt = 0, base_eq = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const bool gt = key[v] > T, eq = key[v] == T;
+        const unsigned bgt = __ballot_sync(FULL, gt), beq = __ballot_sync(FULL, eq);
+        if (gt) out[base_gt + __popc(bgt & lanemask_lt())] = v * 32 + lane;
+        if (eq) {
+            const int slot = base_eq + __popc(beq & lanemask_lt());
+            if (slot < need) out[G2 + slot] = v * 32 + lane;
+        }
+        base_gt += __popc(bgt);
+        base_eq += __popc(beq);
+    }
+}
+
+// ---- layer-1 kNN on raw coordinates: distances on the fly, exact fp32 recipe
+template <int V>
+__global__ void __launch_bounds__(256)
+knn_xyz_kernel(const float *__restrict__ xyz, int point_major, int N, int k, int rows_per_cta, int32_t *__restrict__ idx)
+{
+    extern __shared__ float4 pts[];                               // N x (x, y, z, |p|^2)
+    __shared__ float scratch[8][TOPK_SCRATCH];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (int64_t)b * N * 3;
+    for (int i = tid; i < N; i += 256) {
+        float x, y, z;
+        if (point_major) { x = p[3 * i]; y = p[3 * i + 1]; z = p[3 * i + 2]; }
+        else { x = p[i]; y = p[N + i]; z = p[2 * N + i]; }
+        const float xx = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+        pts[i] = make_float4(x, y, z, xx);
+    }
+    __syncthreads();
+    const int row_begin = blockIdx.x * rows_per_cta;
+    const int row_end = min(row_begin + rows_per_cta, N);
+    for (int i = row_begin + warp; i < row_end; i += 8) {
+        const float4 q = pts[i];
+        float key[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int j = v * 32 + lane;
+            if (j < N) {
+                const float4 c = pts[j];
+                float dot = __fmul_rn(q.x, c.x);
+                dot = __fmaf_rn(q.y, c.y, dot);
+                dot = __fmaf_rn(q.z, c.z, dot);
+                const float inner = __fmul_rn(-2.0f, dot);
+                key[v] = __fsub_rn(__fsub_rn(-c.w, inner), q.w);
+            } else {
+                key[v] = -INFINITY;
+            }
+        }
+        warp_topk<V>(key, k, lane, idx + ((int64_t)b * N + i) * k, scratch[warp]);
+    }
+}
+
+// ---- top-k over rows of a key matrix already in memory (feature-space kNN, knn_point)
+template <int V>
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const float *__restrict__ keys, int64_t rows, int N, int64_t ld, int k, int largest,
+                 int32_t *__restrict__ idx)
+{
+    __shared__ float scratch[8][TOPK_SCRATCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float *kr = keys + row * ld;
+    float key[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int j = v * 32 + lane;
+        const float x = j < N ? __ldcs(kr + j) : 0.0f;
+        key[v] = j < N ? (largest ? x : -x) : -INFINITY;
+    }
+    warp_topk<V>(key, k, lane, idx + row * k, scratch[warp]);
+}
+
+__global__ void sqnorm_rows_kernel(const float *__restrict__ x, int64_t rows, int C, int64_t ld, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) { const float v = x[row * ld + c]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) out[row] = -s;
+}
+
+// ---- EdgeConv aggregation: out[i][c] = act(max_j P[idx[i][j]][c] + Q[i][c]); warp per point
+template <int CPL>
+__global__ void __launch_bounds__(256)
+gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int64_t total, int N,
+                  int k, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ neg_sqnorm)
+{
+    constexpr int Cout = CPL * 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= total) return;
+    const int64_t cloud0 = (i / N) * N;
+    float mx[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) mx[c] = -INFINITY;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+        const int nj = min(32, k - j0);
+        const int my = lane < nj ? idx[i * k + j0 + lane] : 0;
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) {
+            const int64_t src = cloud0 + __shfl_sync(FULL, my, j);
+            const float *pr = PQ + src * ldpq + lane * CPL;
+            if (CPL == 2) {
+                const float2 v = *reinterpret_cast<const float2 *>(pr);
+                mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y);
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPL / 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4 *>(pr + 4 * q);
+                    mx[4 * q] = fmaxf(mx[4 * q], v.x); mx[4 * q + 1] = fmaxf(mx[4 * q + 1], v.y);
+                    mx[4 * q + 2] = fmaxf(mx[4 * q + 2], v.z); mx[4 * q + 3] = fmaxf(mx[4 * q + 3], v.w);
+                }
+            }
+        }
+    }
+    const float *qr = PQ + i * ldpq + Cout + lane * CPL;
+    float ss = 0.0f;
+    float res[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        res[c] = apply_act(mx[c] + qr[c], act);
+        ss = fmaf(res[c], res[c], ss);
+    }
+    float *o = out + i * ldo + lane * CPL;
+    if (CPL == 2) {
+        *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < CPL / 4; ++q)
+            *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    }
+    if (neg_sqnorm) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(FULL, ss, s);
+        if (lane == 0) neg_sqnorm[i] = -ss;
+    }
+}
+
+__global__ void xyz_to_point_major_kernel(const float *__restrict__ cf, int N, float *__restrict__ pm)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float *s = cf + (int64_t)b * 3 * N;
+    float *d = pm + ((int64_t)b * N + i) * 3;
+    d[0] = s[i]; d[1] = s[N + i]; d[2] = s[2 * N + i];
+}
+
+template <typename F>
+int dispatch_v(int64_t N, F &&f)
+{
+    if (N <= 64) return f(std::integral_constant<int, 2>());
+    if (N <= 128) return f(std::integral_constant<int, 4>());
+    if (N <= 256) return f(std::integral_constant<int, 8>());
+    if (N <= 512) return f(std::integral_constant<int, 16>());
+    if (N <= 1024) return f(std::integral_constant<int, 32>());
+    return f(std::integral_constant<int, 64>());
+}
+
+}  // namespace
+
+int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int k, int32_t *idx, cudaStream_t st)
+{
+    ProfileScope _ps("knn_xyz", st);
+    IQ_CHECK(N >= 1 && N <= 2048, "knn: num_points must be in [1,2048]");
+    IQ_CHECK(k >= 1 && k <= N, "knn: k must be in [1,num_points]");
+    IQ_CHECK(B <= 65535, "knn: batch too large for one launch");
+    if (B == 0) return 0;
+    const int rows_per_cta = 64;
+    dim3 grid((unsigned)ceil_div(N, rows_per_cta), (unsigned)B);
+    const size_t smem = sizeof(float4) * (size_t)N;
+    return dispatch_v(N, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        knn_xyz_kernel<V><<<grid, 256, smem, st>>>(xyz, point_major, (int)N, k, rows_per_cta, idx);
+        IQ_COUNT_LAUNCH();
+        IQ_LAUNCH_CHECK();
+        return 0;
+    });
+}
+
+int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx,
+                     cudaStream_t st)
+{
+    ProfileScope _ps("topk_rows", st);
+    IQ_CHECK(N >= 1 && N <= 2048, "topk: row length must be in [1,2048]");
+    IQ_CHECK(k >= 1 && k <= N, "topk: k must be in [1,row length]");
+    if (rows == 0) return 0;
+    const unsigned grid = (unsigned)ceil_div(rows, 8);
+    return dispatch_v(N, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        topk_rows_kernel<V><<<grid, 256, 0, st>>>(keys, rows, (int)N, ld, k, largest, idx);
+        IQ_COUNT_LAUNCH();
+        IQ_LAUNCH_CHECK();
+        return 0;
+    });
+}
+
+int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st)
+{
+    ProfileScope _ps("sqnorm_rows", st);
+    if (rows == 0) return 0;
+    sqnorm_rows_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(x, rows, C, ld, out);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
+                      int act, float *out, int64_t ldo, float *neg_sqnorm, cudaStream_t st)
+{
+    ProfileScope _ps("gather_max", st);
+    const int64_t total = B * N;
+    if (total == 0) return 0;
+    IQ_CHECK(Cout == 64 || Cout == 128 || Cout == 256, "gather_max: Cout must be 64, 128 or 256");
+    IQ_CHECK(ldpq % 4 == 0 && ldo % 4 == 0, "gather_max: leading dimensions must be multiples of 4");
+    const unsigned grid = (unsigned)ceil_div(total * 32, 256);
+    if (Cout == 64) gather_max_kernel<2><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm);
+    else if (Cout == 128) gather_max_kernel<4><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm);
+    else gather_max_kernel<8><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_xyz_to_point_major(const float *x_cf, int64_t B, int64_t N, float *x_pm, cudaStream_t st)
+{
+    ProfileScope _ps("xyz_to_point_major", st);
+    if (B * N == 0) return 0;
+    IQ_CHECK(B <= 65535, "xyz_to_point_major: batch too large");
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)B);
+    xyz_to_point_major_kernel<<<grid, 256, 0, st>>>(x_cf, (int)N, x_pm);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace iq

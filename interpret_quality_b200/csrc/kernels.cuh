@@ -39,6 +39,7 @@ struct GemmDesc {
     int row_group = 1;
     int64_t ld_row_bias = 0;
     int act = ACT_NONE;
+    const char *tag = "sgemm";    // label for the profiling report
     // pooling epilogue: per (m-tile of 128 rows, n) partial max / argmax / sum over the tile's rows
     float *pool_max = nullptr;     // (ceil(M/128), N)
     int32_t *pool_arg = nullptr;   // optional, row index (within the whole M) of the max, lowest on ties

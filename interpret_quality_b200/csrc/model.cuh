@@ -1,0 +1,74 @@
+// Model container of libiq_b200: folded weights on the device + forward orchestration.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace iq {
+
+struct HostTensor {
+    const float *data = nullptr;
+    int64_t numel = 0;
+};
+typedef std::map<std::string, HostTensor> StateDict;
+
+// bump allocator over the caller-provided workspace (no cudaMalloc on the forward path)
+struct Workspace {
+    char *base = nullptr;
+    int64_t size = 0, off = 0;
+    bool dry = false;             // dry run: only measure
+    template <typename T>
+    T *take(int64_t n)
+    {
+        off = round_up(off, 256);
+        T *p = dry ? nullptr : reinterpret_cast<T *>(base + off);
+        off += n * (int64_t)sizeof(T);
+        return p;
+    }
+    bool ok() const { return dry || off <= size; }
+};
+
+// A dense layer with eval-mode BatchNorm folded in: y = act(W' x + b'), W' (cout, cin) row-major.
+struct Dense {
+    float *w = nullptr;
+    float *b = nullptr;
+    int cout = 0, cin = 0;
+};
+
+struct DeviceArena {              // owns every device buffer of a model
+    std::vector<void *> ptrs;
+    ~DeviceArena();
+    int upload(const std::vector<float> &host, float **dev);
+};
+
+class Model {
+public:
+    virtual ~Model() {}
+    virtual const char *kind() const = 0;
+    int num_classes = 10;
+    // largest number of clouds one internal pass handles; forward() loops over chunks
+    int chunk = 64;
+    // bytes of workspace needed to run `B` clouds of `N` points (already capped by chunk)
+    int64_t workspace_bytes(int64_t B, int64_t N);
+    int forward(const float *x, int layout_point_major, int64_t B, int64_t N, float *logits, void *ws, int64_t ws_bytes,
+                float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st);
+
+    DeviceArena arena_;
+
+protected:
+    virtual int plan_and_run(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *logits,
+                             float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st) = 0;
+};
+
+Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int num_classes, std::string &err);
+Model *create_pointnet_model(const StateDict &sd, int num_classes, std::string &err);
+
+// host-side folding helpers (models_common.cu)
+bool fold_dense(const StateDict &sd, const std::string &w_key, const std::string &b_key, const std::string &bn_prefix,
+                int cout, int cin, std::vector<float> &w, std::vector<float> &b, std::string &err);
+
+}  // namespace iq

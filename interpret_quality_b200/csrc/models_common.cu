@@ -1,0 +1,147 @@
+// Shared model plumbing: error state, device arena, BN folding, chunked forward.
+#include <math.h>
+
+#include <mutex>
+
+#include "model.cuh"
+
+namespace iq {
+
+unsigned long long g_launch_count = 0;
+
+static thread_local std::string t_error;
+void set_error(const std::string &msg) { t_error = msg; }
+const char *last_error() { return t_error.c_str(); }
+
+// ---- profiling
+namespace {
+struct ProfEntry { const char *name; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
+std::vector<const char *> g_rep_names;
+}  // namespace
+
+ProfileScope::ProfileScope(const char *name, cudaStream_t s) : slot(-1), st(s)
+{
+    if (!g_prof_on) return;
+    ProfEntry e;
+    e.name = name;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, st);
+    g_prof.push_back(e);
+    slot = (int)g_prof.size() - 1;
+}
+ProfileScope::~ProfileScope()
+{
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+}
+void profile_enable(bool on)
+{
+    for (auto &e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    g_prof.clear();
+    g_prof_on = on;
+}
+int profile_report(const char **names, double *ms, long long *counts, int cap)
+{
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<double, long long>> acc;
+    std::map<std::string, const char *> keep;
+    for (auto &e : g_prof) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) continue;
+        auto &slot = acc[e.name];
+        slot.first += t;
+        slot.second += 1;
+        keep[e.name] = e.name;
+    }
+    int n = 0;
+    for (auto &kv : acc) {
+        if (n < cap) { names[n] = keep[kv.first]; ms[n] = kv.second.first; counts[n] = kv.second.second; }
+        ++n;
+    }
+    return n;
+}
+
+DeviceArena::~DeviceArena()
+{
+    for (void *p : ptrs) cudaFree(p);
+}
+
+int DeviceArena::upload(const std::vector<float> &host, float **dev)
+{
+    void *p = nullptr;
+    IQ_CUDA(cudaMalloc(&p, sizeof(float) * std::max<size_t>(host.size(), 1)));
+    ptrs.push_back(p);
+    IQ_CUDA(cudaMemcpy(p, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
+    *dev = reinterpret_cast<float *>(p);
+    return 0;
+}
+
+// y = bn(W x + b) with eval statistics  ->  W' = s*W, b' = s*b + (beta - mean*s), s = gamma / sqrt(var + 1e-5).
+// (BatchNorm eps 1e-5 is the nn.BatchNorm default the reference uses everywhere.)  Folded in double, rounded once.
+bool fold_dense(const StateDict &sd, const std::string &w_key, const std::string &b_key, const std::string &bn_prefix,
+                int cout, int cin, std::vector<float> &w, std::vector<float> &b, std::string &err)
+{
+    auto need = [&](const std::string &k, int64_t n) -> const float * {
+        auto it = sd.find(k);
+        if (it == sd.end()) { err = "state dict is missing '" + k + "'"; return nullptr; }
+        if (it->second.numel != n) {
+            err = "'" + k + "' has " + std::to_string(it->second.numel) + " elements, expected " + std::to_string(n);
+            return nullptr;
+        }
+        return it->second.data;
+    };
+    const float *W = need(w_key, (int64_t)cout * cin);
+    if (!W) return false;
+    const float *bias = nullptr;
+    if (!b_key.empty()) { bias = need(b_key, cout); if (!bias) return false; }
+    const float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
+    if (!bn_prefix.empty()) {
+        gamma = need(bn_prefix + ".weight", cout);
+        beta = need(bn_prefix + ".bias", cout);
+        mean = need(bn_prefix + ".running_mean", cout);
+        var = need(bn_prefix + ".running_var", cout);
+        if (!gamma || !beta || !mean || !var) return false;
+    }
+    w.resize((size_t)cout * cin);
+    b.resize(cout);
+    for (int o = 0; o < cout; ++o) {
+        double s = 1.0, t = 0.0;
+        if (gamma) {
+            s = (double)gamma[o] / sqrt((double)var[o] + 1e-5);
+            t = (double)beta[o] - (double)mean[o] * s;
+        }
+        for (int i = 0; i < cin; ++i) w[(size_t)o * cin + i] = (float)(s * (double)W[(size_t)o * cin + i]);
+        b[o] = (float)(s * (bias ? (double)bias[o] : 0.0) + t);
+    }
+    return true;
+}
+
+int64_t Model::workspace_bytes(int64_t B, int64_t N)
+{
+    Workspace ws;
+    ws.dry = true;
+    const int64_t Bc = std::min<int64_t>(std::max<int64_t>(B, 1), chunk);
+    if (plan_and_run(ws, nullptr, 1, Bc, N, nullptr, nullptr, nullptr, nullptr) != 0) return -1;
+    return round_up(ws.off, 256) + 256;
+}
+
+int Model::forward(const float *x, int point_major, int64_t B, int64_t N, float *logits, void *wsp, int64_t ws_bytes,
+                   float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st)
+{
+    IQ_CHECK(x && logits, "forward: null input or output");
+    IQ_CHECK(wsp || B == 0, "forward: null workspace");
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t Bc = std::min<int64_t>(chunk, B - b0);
+        Workspace ws;
+        ws.base = reinterpret_cast<char *>(wsp);
+        ws.size = ws_bytes;
+        const int rc = plan_and_run(ws, x + b0 * N * 3, point_major, Bc, N, logits + b0 * num_classes,
+                                    aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
+                                    aux_crt ? aux_crt + b0 * 1024 : nullptr, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+}  // namespace iq

@@ -220,6 +220,7 @@ __global__ void pool_finish_kernel(const float *__restrict__ pmax, const int32_t
 
 int launch_sgemm(const GemmDesc &g, cudaStream_t st)
 {
+    ProfileScope _ps(g.tag, st);
     IQ_CHECK(g.M >= 0 && g.N >= 0 && g.K >= 1 && g.batch >= 1, "sgemm: bad shape");
     if (g.M == 0 || g.N == 0) return 0;
     IQ_CHECK(g.C || g.pool_max, "sgemm: no output requested");
@@ -240,6 +241,7 @@ int launch_pool_finish(const float *pmax, const int32_t *parg, const float *psum
                        int rows_per_group, int N, float *out_max, int64_t ld_max, int64_t *out_arg, float *out_mean,
                        int64_t ld_mean, cudaStream_t st)
 {
+    ProfileScope _ps("pool_finish", st);
     if (groups == 0) return 0;
     IQ_CHECK(groups <= 65535, "pool_finish: too many groups");
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)groups);

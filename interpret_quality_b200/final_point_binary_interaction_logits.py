@@ -1,0 +1,46 @@
+"""compute_order_interaction_logits with the reference's signature
+(final_point_binary_interaction_logits.py:15-70 of ada-shen/Interpret_quality)."""
+import numpy as np
+import torch
+
+from . import ops
+from .tools.final_common import _device_of
+
+# contexts evaluated per internal pass; independent of args.interaction_batch_size
+ENGINE_CONTEXTS_PER_PASS = 128
+
+
+def compute_order_interaction_logits(model, data_disturb, region_id, region_pair_list, context_list, args,
+                                     pair_slice=None):
+    """Logits of the four coalitions S+{i,j}, S+{i}, S+{j}, S of every (pair, context).
+
+    data_disturb (1,N,3); region_id (N,) ndarray; region_pair_list (P,2); context_list (P,ctx,m) (m may
+    be 0, dtype may be float64 then).  Returns a float32 CUDA tensor (P, 4*ctx, C), rows 4k..4k+3 in
+    the order above.  pair_slice (start, stop) restricts the work to a shard of the pairs (used by
+    distributed.py); rows of other pairs are left zero.
+    """
+    dev = _device_of(model)
+    R = int(getattr(args, "num_regions", 0) or int(np.max(region_id)) + 1)
+    data = data_disturb.to(dev, torch.float32, non_blocking=True).reshape(-1, 3).contiguous()
+    N = data.shape[0]
+    pairs = np.asarray(region_pair_list).astype(np.int64)
+    ctxs = np.asarray(context_list)
+    P, ctx = pairs.shape[0], ctxs.shape[1]
+    m = ctxs.shape[2] if ctxs.ndim == 3 else 0
+    ctx_d = ops.to_dev_i64(ctxs.reshape(P, ctx, m), dev)
+    region_d = ops.to_dev_i64(region_id, dev)
+    center = ops.center(data)
+    C = model.output_channels
+    out = torch.zeros((P, 4 * ctx, C), dtype=torch.float32, device=dev)
+    lo, hi = pair_slice if pair_slice is not None else (0, P)
+    step = ENGINE_CONTEXTS_PER_PASS
+    masked = torch.empty((4 * min(step, max(ctx, 1)), N, 3), dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        for p in range(lo, hi):
+            for s in range(0, ctx, step):
+                cb = ctx_d[p, s:s + step].contiguous()
+                rows = 4 * cb.shape[0]
+                ops.mask_interaction(data, center, cb, pairs[p, 0], pairs[p, 1], region_d, R, point_major=True,
+                                     out=masked[:rows])
+                model.forward_point_major(masked[:rows], out=out[p, 4 * s:4 * s + rows])
+    return out

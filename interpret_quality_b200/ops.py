@@ -1,0 +1,172 @@
+"""Tensor-level wrappers over the C ABI: argument checking + pointer marshalling.
+
+torch is used for device memory and streams only; all arithmetic happens in
+libiq_b200.so.  Every function requires CUDA tensors and raises otherwise.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.IQError("%s must live on a CUDA device (iq_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def to_dev_i64(a, device):
+    """numpy / tensor integer array -> contiguous int64 CUDA tensor."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.int64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int64)).to(device)
+
+
+def fps(xyz, npoint):
+    _chk(xyz, torch.float32, "xyz")
+    B, N, C = xyz.shape
+    if C != 3:
+        raise ValueError("xyz must be (B,N,3)")
+    out = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    _lib.check(_lib.load().iq_fps(xyz.data_ptr(), B, N, npoint, out.data_ptr(), _stream()))
+    return out
+
+
+def square_distance3(src, dst):
+    _chk(src, torch.float32, "src")
+    _chk(dst, torch.float32, "dst")
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    _lib.check(_lib.load().iq_square_distance3(src.data_ptr(), dst.data_ptr(), B, N, M, out.data_ptr(), _stream()))
+    return out
+
+
+def region_id(xyz, fps_index):
+    _chk(xyz, torch.float32, "xyz")
+    _chk(fps_index, torch.int64, "fps_index")
+    N = xyz.shape[-2]
+    out = torch.empty((N,), dtype=torch.int64, device=xyz.device)
+    _lib.check(_lib.load().iq_region_id(xyz.data_ptr(), fps_index.data_ptr(), N, fps_index.numel(), out.data_ptr(),
+                                        _stream()))
+    return out
+
+
+def center(xyz):
+    _chk(xyz, torch.float32, "xyz")
+    N = xyz.shape[-2]
+    out = torch.empty((3,), dtype=torch.float32, device=xyz.device)
+    _lib.check(_lib.load().iq_center(xyz.data_ptr(), N, out.data_ptr(), _stream()))
+    return out
+
+
+def mask_shapley(data, center_t, orders, region_ids, out=None, in_place=False):
+    """data (N,3) | None, center (3), orders (bs,R) i64, region_ids (N) i64 -> ((R+1)*bs, N, 3)."""
+    _chk(center_t, torch.float32, "center")
+    _chk(orders, torch.int64, "orders")
+    _chk(region_ids, torch.int64, "region_id")
+    bs, R = orders.shape
+    N = region_ids.numel()
+    if in_place:
+        _chk(out, torch.float32, "masked_data")
+        if out.numel() != (R + 1) * bs * N * 3:
+            raise ValueError("masked_data must be ((num_regions+1)*bs, num_points, 3)")
+        dptr = 0
+    else:
+        _chk(data, torch.float32, "data")
+        if out is None:
+            out = torch.empty(((R + 1) * bs, N, 3), dtype=torch.float32, device=data.device)
+        dptr = data.data_ptr()
+    _lib.check(_lib.load().iq_mask_shapley(dptr, center_t.data_ptr(), orders.data_ptr(), region_ids.data_ptr(), bs, R,
+                                           N, out.data_ptr(), 1 if in_place else 0, _stream()))
+    return out
+
+
+def mask_interaction(data, center_t, contexts, region_i, region_j, region_ids, num_regions, point_major=False,
+                     out=None):
+    """data (N,3), contexts (ctx,m) i64 -> (4*ctx,3,N) (reference layout) or (4*ctx,N,3)."""
+    _chk(data, torch.float32, "data")
+    _chk(center_t, torch.float32, "center")
+    _chk(contexts, torch.int64, "contexts")
+    _chk(region_ids, torch.int64, "region_id")
+    ctx, m = contexts.shape
+    N = region_ids.numel()
+    if out is None:
+        shape = (4 * ctx, N, 3) if point_major else (4 * ctx, 3, N)
+        out = torch.empty(shape, dtype=torch.float32, device=data.device)
+    cptr = contexts.data_ptr() if contexts.numel() else 0
+    _lib.check(_lib.load().iq_mask_interaction(data.data_ptr(), center_t.data_ptr(), cptr, ctx, m, int(region_i),
+                                               int(region_j), region_ids.data_ptr(), num_regions, N,
+                                               1 if point_major else 0, out.data_ptr(), _stream()))
+    return out
+
+
+def reward(logits, lbl, softmax_type="modified", out=None):
+    _chk(logits, torch.float32, "logits")
+    B, C = logits.shape
+    if out is None:
+        out = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().iq_reward(logits.data_ptr(), B, C, int(lbl), 1 if softmax_type == "normal" else 0,
+                                     out.data_ptr(), _stream()))
+    return out
+
+
+def shapley_accumulate(v, orders, phi_sum):
+    _chk(v, torch.float32, "v")
+    _chk(orders, torch.int64, "orders")
+    _chk(phi_sum, torch.float64, "phi_sum")
+    bs, R = orders.shape
+    if v.numel() != bs * (R + 1) or phi_sum.numel() != R:
+        raise ValueError("shape mismatch in shapley_accumulate")
+    _lib.check(_lib.load().iq_shapley_accumulate(v.data_ptr(), orders.data_ptr(), bs, R, phi_sum.data_ptr(), _stream()))
+    return phi_sum
+
+
+def interaction_reduce(all_logits, lbl, softmax_type="modified"):
+    _chk(all_logits, torch.float32, "all_logits")
+    P, rows, C = all_logits.shape
+    ctx = rows // 4
+    out = torch.empty((P, ctx), dtype=torch.float64, device=all_logits.device)
+    _lib.check(_lib.load().iq_interaction_reduce(all_logits.data_ptr(), P, ctx, C, int(lbl),
+                                                 1 if softmax_type == "normal" else 0, out.data_ptr(), _stream()))
+    return out
+
+
+def knn_xyz(xyz, k):
+    """xyz (B,N,3) point-major -> (B,N,k) int32 neighbour sets (models/dgcnn.py:12-18 for 3-d input)."""
+    _chk(xyz, torch.float32, "xyz")
+    B, N, _ = xyz.shape
+    out = torch.empty((B, N, k), dtype=torch.int32, device=xyz.device)
+    _lib.check(_lib.load().iq_knn_xyz(xyz.data_ptr(), B, N, k, out.data_ptr(), _stream()))
+    return out
+
+
+def topk_rows(keys, k, largest=True):
+    """keys (rows,N) -> (rows,k) int32, unordered exact top-k with lowest-index tie-breaking."""
+    _chk(keys, torch.float32, "keys")
+    rows, N = keys.shape
+    out = torch.empty((rows, k), dtype=torch.int32, device=keys.device)
+    _lib.check(_lib.load().iq_topk_rows(keys.data_ptr(), rows, N, N, k, 1 if largest else 0, out.data_ptr(), _stream()))
+    return out
+
+
+def linear(x, w, b=None, act=0, engine=0):
+    """act(x @ w.T + b) through the library's GEMM (engine 0: exact fp32 SIMT, 1: tcgen05 3xTF32)."""
+    _chk(x, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    bp = _chk(b, torch.float32, "b").data_ptr() if b is not None else 0
+    _lib.check(_lib.load().iq_linear(x.data_ptr(), w.data_ptr(), bp, M, N, K, act, engine, y.data_ptr(), _stream()))
+    return y
