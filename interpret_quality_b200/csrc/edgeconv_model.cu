@@ -31,8 +31,29 @@ public:
     const char *kind() const override { return dynamic ? "dgcnn" : "gcnn"; }
 
 protected:
-    int plan_and_run(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *logits, float *,
-                     int64_t *, cudaStream_t st) override
+    int pooled_dim() const override { return 2048; }
+
+    int run_head(Workspace &ws, const float *g, int64_t B, float *logits, cudaStream_t st) override
+    {
+        float *h1 = ws.take<float>(B * 512);
+        float *h2 = ws.take<float>(B * 256);
+        IQ_CHECK(ws.ok(), "dgcnn/gcnn: workspace too small");
+        if (ws.dry) return 0;
+        const Dense *head[3] = {&lin1, &lin2, &lin3};
+        const float *hin[3] = {g, h1, h2};
+        float *hout[3] = {h1, h2, logits};
+        for (int i = 0; i < 3; ++i) {
+            GemmDesc h;
+            h.A = hin[i]; h.lda = head[i]->cin; h.B = head[i]->w; h.ldb = head[i]->cin;
+            h.C = hout[i]; h.ldc = head[i]->cout; h.M = (int)B; h.N = head[i]->cout; h.K = head[i]->cin;
+            h.bias = head[i]->b; h.act = i < 2 ? ACT_LRELU : ACT_NONE; h.tag = "sgemm_head";
+            if (int rc = launch_sgemm(h, st)) return rc;
+        }
+        return 0;
+    }
+
+    int run_body(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *g, float *,
+                 int64_t *, cudaStream_t st) override
     {
         IQ_CHECK(N % 128 == 0, "dgcnn/gcnn: num_points must be a multiple of 128");
         IQ_CHECK(N <= 2048, "dgcnn/gcnn: num_points must be <= 2048");
@@ -47,9 +68,6 @@ protected:
         const int tiles = (int)(N / 128);
         float *pmax = ws.take<float>(Bc * tiles * 1024);
         float *psum = ws.take<float>(Bc * tiles * 1024);
-        float *g = ws.take<float>(Bc * 2048);
-        float *h1 = ws.take<float>(Bc * 512);
-        float *h2 = ws.take<float>(Bc * 256);
         IQ_CHECK(ws.ok(), "dgcnn/gcnn: workspace too small");
         if (ws.dry) return 0;
 
@@ -87,16 +105,6 @@ protected:
         if (int rc = launch_sgemm(c5, st)) return rc;
         if (int rc = launch_pool_finish(pmax, nullptr, psum, Bc, tiles, (int)N, 1024, g, 2048, nullptr, g + 1024, 2048, st))
             return rc;
-        const Dense *head[3] = {&lin1, &lin2, &lin3};
-        const float *hin[3] = {g, h1, h2};
-        float *hout[3] = {h1, h2, logits};
-        for (int i = 0; i < 3; ++i) {
-            GemmDesc h;
-            h.A = hin[i]; h.lda = head[i]->cin; h.B = head[i]->w; h.ldb = head[i]->cin;
-            h.C = hout[i]; h.ldc = head[i]->cout; h.M = (int)Bc; h.N = head[i]->cout; h.K = head[i]->cin;
-            h.bias = head[i]->b; h.act = i < 2 ? ACT_LRELU : ACT_NONE; h.tag = "sgemm_head";
-            if (int rc = launch_sgemm(h, st)) return rc;
-        }
         return 0;
     }
 };

@@ -1,0 +1,480 @@
+// tcgen05 / TMEM / TMA GEMM with 3xTF32 error compensation (sm_100a only).
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]          A (M,K), B (N,K) both K-major fp32
+//
+// Single-pass TF32 (and BF16) fails the 1e-3 parity bar for every model of the
+// reference, DGCNN worst because a rounded kNN key flips neighbours
+// (SURVEY.md section 7.2), so each fp32 operand is pre-split by its producer into
+// hi = tf32(x) and lo = tf32(x - hi) and the tile accumulates
+//   Alo*Bhi + Ahi*Blo + Ahi*Bhi      (fp32 accumulation in TMEM).
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of Ahi/Alo/Bhi/Blo
+//               into a multi-stage shared-memory ring, mbarrier complete_tx.
+//   warp 1      TMEM allocation; one elected lane issues tcgen05.mma.kind::tf32
+//               (M=128, N=BN, K=8) x 4 k-steps x 3 split terms per stage, tcgen05.commit
+//               releases the stage / publishes the accumulator.
+//   warps 2-5   epilogue: tcgen05.ld 32x32b (thread = accumulator row), fused
+//               scale / bias / activation, then either
+//                 STORE  row-major fp32 store (EdgeConv P|Q rows, kNN keys 2*G - |x_j|^2), or
+//                 POOL   rows are output channels, columns are the points of one cloud:
+//                        running max / argmax / sum over all column tiles of the cloud, i.e.
+//                        conv + BN + activation + global max/avg pooling without ever
+//                        writing the (B, C, N) tensor (models/dgcnn.py:108-111,
+//                        models/pointnet.py:35,83 of the reference).
+//   Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i
+//   overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace iq {
+
+namespace {
+
+constexpr int TBM = 128;          // UMMA M (rows of A per tile)
+constexpr int TBK = 32;           // fp32 per 128-byte swizzle row
+constexpr int UMMA_K = 8;         // K of one tcgen05.mma.kind::tf32
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                       // leading byte offset: unused for swizzled K-major (canonical 1)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6), a/b format TF32 = 2 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+}
+
+struct TcParams {
+    int K;                       // multiple of 32
+    int mode;                    // 0 = STORE, 1 = POOL
+    // STORE: units = (M/128) * (Ncols/BN), one accumulator tile each
+    int n_tiles;                 // Ncols / BN
+    int rows_per_batch;          // > 0: B rows live in the same batch as the A rows (Gram), else B is shared
+    // POOL: units = clouds * (Cout/128); tiles_per_unit = points / BN
+    int m_tiles;                 // Cout / 128
+    int points;                  // points per cloud
+    int num_units, tiles_per_unit;
+    float alpha;
+    const float *bias;           // STORE: per column (index b_row0 + c), POOL: per row (channel)
+    int act;
+    float *C;                    // STORE output
+    int64_t ldc;
+    float *out_max;              // POOL outputs, (clouds, ld_out)
+    float *out_mean;
+    int64_t *out_arg;            // (clouds, Cout)
+    int64_t ld_out;
+    int cout;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+    static constexpr int A_BYTES = TBM * TBK * 4;
+    static constexpr int B_BYTES = BN * TBK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+               const TcParams p)
+{
+    using S = TcSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.K / TBK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_ahi); prefetch_tmap(&map_alo); prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 2 * BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto tile_rows = [&](int unit, int j, int &a_row0, int &b_row0) {
+        if (p.mode == 0) {
+            const int mt = unit / p.n_tiles, nt = unit - mt * p.n_tiles;
+            a_row0 = mt * TBM;
+            b_row0 = nt * BN + (p.rows_per_batch > 0 ? (a_row0 / p.rows_per_batch) * p.rows_per_batch : 0);
+        } else {
+            const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
+            a_row0 = mt * TBM;
+            b_row0 = cloud * p.points + j * BN;
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
+                for (int j = 0; j < p.tiles_per_unit; ++j) {
+                    int a_row0, b_row0;
+                    tile_rows(unit, j, a_row0, b_row0);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t *st = smem + stage * S::STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                        tma_load_2d(st, &map_ahi, &full_bar[stage], kb * TBK, a_row0);
+                        tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * TBK, a_row0);
+                        tma_load_2d(st + 2 * S::A_BYTES, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
+                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_blo, &full_bar[stage], kb * TBK, b_row0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
+                for (int j = 0; j < p.tiles_per_unit; ++j) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
+                        const uint64_t ahi = make_smem_desc(sbase), alo = make_smem_desc(sbase + S::A_BYTES);
+                        const uint64_t bhi = make_smem_desc(sbase + 2 * S::A_BYTES);
+                        const uint64_t blo = make_smem_desc(sbase + 2 * S::A_BYTES + S::B_BYTES);
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {            // small terms first
+                            const uint64_t ad = term == 0 ? alo : ahi;
+                            const uint64_t bd = term == 1 ? blo : bhi;
+#pragma unroll
+                            for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
+                                const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                                umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);                  // frees the stage when the MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&tmem_full[acc]);                        // accumulator complete
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+        }
+    } else {
+        const int quad = warp & 3;                                       // TMEM lane quadrant this warp may read
+        const int row_in_tile = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            float run_max = -INFINITY, run_sum = 0.0f;
+            int run_arg = 0;
+            for (int j = 0; j < p.tiles_per_unit; ++j) {
+                int a_row0, b_row0;
+                tile_rows(unit, j, a_row0, b_row0);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+                if (p.mode == 0) {
+                    const int nt = unit % p.n_tiles;
+                    float *crow = p.C + (int64_t)(a_row0 + row_in_tile) * p.ldc + (int64_t)nt * BN;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float b = p.bias ? __ldg(p.bias + b_row0 + c0 + i) : 0.0f;
+                            v[i] = apply_act(fmaf(p.alpha, v[i], b), p.act);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4 *>(crow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                } else {
+                    const float b = p.bias ? __ldg(p.bias + a_row0 + row_in_tile) : 0.0f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float y = apply_act(fmaf(p.alpha, v[i], b), p.act);
+                            if (y > run_max) { run_max = y; run_arg = j * BN + c0 + i; }
+                            run_sum += y;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (p.mode == 1) {
+                const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
+                const int ch = mt * TBM + row_in_tile;
+                p.out_max[(int64_t)cloud * p.ld_out + ch] = run_max;
+                if (p.out_mean) p.out_mean[(int64_t)cloud * p.ld_out + ch] = run_sum / (float)p.points;
+                if (p.out_arg) p.out_arg[(int64_t)cloud * p.cout + ch] = run_arg;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ------------------------------------------------------------------ hi/lo split
+__device__ __forceinline__ float tf32_round(float x)
+{
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+__global__ void split_tf32_kernel(const float *__restrict__ x, int64_t rows, int cols, int64_t ldx,
+                                  float *__restrict__ hi, float *__restrict__ lo, int64_t ldo)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cv = cols >> 2;
+    if (t >= rows * cv) return;
+    const int64_t r = t / cv;
+    const int c = (int)(t - r * cv) << 2;
+    const float4 v = *reinterpret_cast<const float4 *>(x + r * ldx + c);
+    float4 h, l;
+    h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
+    h.y = tf32_round(v.y); l.y = tf32_round(v.y - h.y);
+    h.z = tf32_round(v.z); l.z = tf32_round(v.z - h.z);
+    h.w = tf32_round(v.w); l.w = tf32_round(v.w - h.w);
+    *reinterpret_cast<float4 *>(hi + r * ldo + c) = h;
+    *reinterpret_cast<float4 *>(lo + r * ldo + c) = l;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D map over a K-major fp32 matrix (rows, K) with leading dimension ld; box = 32 x box_rows, 128B swizzle
+int make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int64_t ld, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    IQ_CHECK(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    IQ_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0, "gemm_tc: operand must be 16-byte aligned");
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IQ_CHECK(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 0;
+}
+
+int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float *hi, float *lo, int64_t ldo,
+                      cudaStream_t st)
+{
+    ProfileScope _ps("split_tf32", st);
+    IQ_CHECK(cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "split_tf32: widths must be multiples of 4");
+    if (rows == 0) return 0;
+    const int64_t n = rows * (cols / 4);
+    split_tf32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, rows, cols, ldx, hi, lo, ldo);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
+bool tc_gemm_supported(const TcGemm &g)
+{
+    if (g.K % TBK != 0 || g.K < TBK) return false;
+    if (g.mode == 0) return g.M % TBM == 0 && g.N % 128 == 0;
+    return g.cout % TBM == 0 && g.points % 128 == 0 && g.clouds >= 1;
+}
+
+int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
+{
+    ProfileScope _ps(g.tag, st);
+    IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape (M % 128, N % 128, K % 32 must be 0)");
+    constexpr int BN = 128, STAGES = 3;
+    using S = TcSmem<BN, STAGES>;
+    TcParams p = {};
+    p.K = g.K; p.mode = g.mode; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
+    int64_t a_rows, b_rows;
+    if (g.mode == 0) {
+        p.n_tiles = g.N / BN; p.rows_per_batch = g.rows_per_batch; p.C = g.C; p.ldc = g.ldc;
+        p.num_units = (g.M / TBM) * p.n_tiles; p.tiles_per_unit = 1;
+        a_rows = g.M;
+        b_rows = g.rows_per_batch > 0 ? g.M : g.N;
+        IQ_CHECK(g.C && g.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0, "gemm_tc: C must be 16-byte aligned");
+    } else {
+        p.m_tiles = g.cout / TBM; p.points = g.points; p.cout = g.cout;
+        p.num_units = g.clouds * p.m_tiles; p.tiles_per_unit = g.points / BN;
+        p.out_max = g.out_max; p.out_mean = g.out_mean; p.out_arg = g.out_arg; p.ld_out = g.ld_out;
+        a_rows = g.cout;
+        b_rows = (int64_t)g.clouds * g.points;
+        IQ_CHECK(g.out_max, "gemm_tc: pooling output missing");
+    }
+    if (p.num_units == 0) return 0;
+    CUtensorMap mahi, malo, mbhi, mblo;
+    if (int rc = make_map(&mahi, g.A_hi, a_rows, g.K, g.lda, TBM)) return rc;
+    if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
+    if (int rc = make_map(&mbhi, g.B_hi, b_rows, g.K, g.ldb, BN)) return rc;
+    if (int rc = make_map(&mblo, g.B_lo, b_rows, g.K, g.ldb, BN)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    const int grid = std::min(p.num_units, sm_count());
+    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(mahi, malo, mbhi, mblo, p);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace iq

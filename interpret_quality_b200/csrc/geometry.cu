@@ -92,7 +92,10 @@ int launch_fps(const float *xyz, int64_t B, int64_t N, int64_t npoint, int64_t *
     if (N <= 512) fps_kernel<2><<<grid, 256, smem, st>>>(xyz, (int)N, (int)npoint, idx64, idx32, new_xyz);
     else if (N <= 1024) fps_kernel<4><<<grid, 256, smem, st>>>(xyz, (int)N, (int)npoint, idx64, idx32, new_xyz);
     else if (N <= 2048) fps_kernel<8><<<grid, 256, smem, st>>>(xyz, (int)N, (int)npoint, idx64, idx32, new_xyz);
-    else fps_kernel<16><<<grid, 256, smem, st>>>(xyz, (int)N, (int)npoint, idx64, idx32, new_xyz);
+    else {
+        IQ_CUDA(cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_kernel<16><<<grid, 256, smem, st>>>(xyz, (int)N, (int)npoint, idx64, idx32, new_xyz);
+    }
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;

@@ -195,7 +195,8 @@ __global__ void sqnorm_rows_kernel(const float *__restrict__ x, int64_t rows, in
 template <int CPL>
 __global__ void __launch_bounds__(256)
 gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int64_t total, int N,
-                  int k, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ neg_sqnorm)
+                  int k, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ neg_sqnorm,
+                  float *__restrict__ out_hi, float *__restrict__ out_lo)
 {
     constexpr int Cout = CPL * 32;
     const int lane = threadIdx.x & 31;
@@ -240,6 +241,15 @@ gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__r
 #pragma unroll
         for (int q = 0; q < CPL / 4; ++q)
             *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    }
+    if (out_hi) {                                                   // tf32 hi/lo split for the tensor-core consumers
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const float h = __uint_as_float((__float_as_uint(res[c]) + 0x1000u) & 0xffffe000u);
+            const float l = res[c] - h;
+            out_hi[i * ldo + lane * CPL + c] = h;
+            out_lo[i * ldo + lane * CPL + c] = __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+        }
     }
     if (neg_sqnorm) {
 #pragma unroll
@@ -318,7 +328,8 @@ int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *o
 }
 
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
-                      int act, float *out, int64_t ldo, float *neg_sqnorm, cudaStream_t st)
+                      int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,
+                      cudaStream_t st)
 {
     ProfileScope _ps("gather_max", st);
     const int64_t total = B * N;
@@ -326,9 +337,9 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
     IQ_CHECK(Cout == 64 || Cout == 128 || Cout == 256, "gather_max: Cout must be 64, 128 or 256");
     IQ_CHECK(ldpq % 4 == 0 && ldo % 4 == 0, "gather_max: leading dimensions must be multiples of 4");
     const unsigned grid = (unsigned)ceil_div(total * 32, 256);
-    if (Cout == 64) gather_max_kernel<2><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm);
-    else if (Cout == 128) gather_max_kernel<4><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm);
-    else gather_max_kernel<8><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm);
+    if (Cout == 64) gather_max_kernel<2><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
+    else if (Cout == 128) gather_max_kernel<4><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
+    else gather_max_kernel<8><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;

@@ -50,13 +50,41 @@ int launch_pool_finish(const float *pmax, const int32_t *parg, const float *psum
                        int rows_per_group, int N, float *out_max, int64_t ld_max, int64_t *out_arg, float *out_mean,
                        int64_t ld_mean, cudaStream_t st);
 
+// gemm_tc.cu -- tcgen05 3xTF32 GEMM on pre-split (hi, lo) operands
+struct TcGemm {
+    const float *A_hi = nullptr, *A_lo = nullptr;   // (rows, K) K-major, leading dimension lda
+    const float *B_hi = nullptr, *B_lo = nullptr;   // (rows, K) K-major, leading dimension ldb
+    int64_t lda = 0, ldb = 0;
+    int K = 0;
+    int mode = 0;                 // 0 = STORE: C = act(alpha * A B^T + bias[col]);  1 = POOL (see gemm_tc.cu)
+    // STORE
+    int M = 0, N = 0;             // A rows, output columns
+    int rows_per_batch = 0;       // > 0: batched Gram, B rows taken from the batch the A rows belong to
+    float *C = nullptr;
+    int64_t ldc = 0;
+    // POOL: A = weights (cout, K), B = activations (clouds * points, K); reduces over the points of each cloud
+    int clouds = 0, points = 0, cout = 0;
+    float *out_max = nullptr, *out_mean = nullptr;
+    int64_t *out_arg = nullptr;
+    int64_t ld_out = 0;
+    float alpha = 1.0f;
+    const float *bias = nullptr;  // STORE: per output column; POOL: per output channel
+    int act = ACT_NONE;
+    const char *tag = "gemm_tc";
+};
+bool tc_gemm_supported(const TcGemm &g);
+int launch_gemm_tc(const TcGemm &g, cudaStream_t st);
+int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float *hi, float *lo, int64_t ldo,
+                      cudaStream_t st);
+
 // graph.cu
 int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int k, int32_t *idx, cudaStream_t st);
 int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx,
                      cudaStream_t st);
 int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st);
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
-                      int act, float *out, int64_t ldo, float *neg_sqnorm, cudaStream_t st);
+                      int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,
+                      cudaStream_t st);
 int launch_xyz_to_point_major(const float *x_cf, int64_t B, int64_t N, float *x_pm, cudaStream_t st);
 
 }  // namespace iq

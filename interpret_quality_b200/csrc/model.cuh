@@ -60,8 +60,15 @@ public:
     DeviceArena arena_;
 
 protected:
-    virtual int plan_and_run(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *logits,
-                             float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st) = 0;
+    // width of the pooled per-cloud feature the body hands to the head
+    virtual int pooled_dim() const = 0;
+    // body: point-wise layers + pooling for a chunk of Bc clouds -> pooled (Bc, pooled_dim())
+    virtual int run_body(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *pooled,
+                         float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st) = 0;
+    // head: the classifier MLP over all B clouds at once (M = B keeps the GEMM grid filled)
+    virtual int run_head(Workspace &ws, const float *pooled, int64_t B, float *logits, cudaStream_t st) = 0;
+    int plan(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits, float *aux_trans_feat,
+             int64_t *aux_crt, cudaStream_t st);
 };
 
 Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int num_classes, std::string &err);

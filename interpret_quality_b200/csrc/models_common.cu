@@ -117,12 +117,35 @@ bool fold_dense(const StateDict &sd, const std::string &w_key, const std::string
     return true;
 }
 
+int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,
+                float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st)
+{
+    float *pooled = ws.take<float>(B * pooled_dim());
+    const int64_t head_mark = ws.off;
+    int64_t peak = ws.off;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t Bc = std::min<int64_t>(chunk, B - b0);
+        ws.off = head_mark;                                        // every chunk reuses the same scratch
+        const int rc = run_body(ws, ws.dry ? nullptr : x + b0 * N * 3, point_major, Bc, N,
+                                ws.dry ? nullptr : pooled + b0 * pooled_dim(),
+                                aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
+                                aux_crt ? aux_crt + b0 * 1024 : nullptr, st);
+        if (rc != 0) return rc;
+        peak = std::max(peak, ws.off);
+        if (ws.dry) break;                                         // the first chunk is the largest
+    }
+    ws.off = head_mark;
+    const int rc = run_head(ws, pooled, B, logits, st);
+    if (rc != 0) return rc;
+    ws.off = std::max(peak, ws.off);
+    return 0;
+}
+
 int64_t Model::workspace_bytes(int64_t B, int64_t N)
 {
     Workspace ws;
     ws.dry = true;
-    const int64_t Bc = std::min<int64_t>(std::max<int64_t>(B, 1), chunk);
-    if (plan_and_run(ws, nullptr, 1, Bc, N, nullptr, nullptr, nullptr, nullptr) != 0) return -1;
+    if (plan(ws, nullptr, 1, std::max<int64_t>(B, 1), N, nullptr, nullptr, nullptr, nullptr) != 0) return -1;
     return round_up(ws.off, 256) + 256;
 }
 
@@ -130,18 +153,12 @@ int Model::forward(const float *x, int point_major, int64_t B, int64_t N, float 
                    float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st)
 {
     IQ_CHECK(x && logits, "forward: null input or output");
-    IQ_CHECK(wsp || B == 0, "forward: null workspace");
-    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
-        const int64_t Bc = std::min<int64_t>(chunk, B - b0);
-        Workspace ws;
-        ws.base = reinterpret_cast<char *>(wsp);
-        ws.size = ws_bytes;
-        const int rc = plan_and_run(ws, x + b0 * N * 3, point_major, Bc, N, logits + b0 * num_classes,
-                                    aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
-                                    aux_crt ? aux_crt + b0 * 1024 : nullptr, st);
-        if (rc != 0) return rc;
-    }
-    return 0;
+    if (B == 0) return 0;
+    IQ_CHECK(wsp, "forward: null workspace");
+    Workspace ws;
+    ws.base = reinterpret_cast<char *>(wsp);
+    ws.size = ws_bytes;
+    return plan(ws, x, point_major, B, N, logits, aux_trans_feat, aux_crt, st);
 }
 
 }  // namespace iq

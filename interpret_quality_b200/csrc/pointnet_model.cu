@@ -76,8 +76,21 @@ protected:
         return launch_sgemm(g, st);
     }
 
-    int plan_and_run(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *logits,
-                     float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st) override
+    int pooled_dim() const override { return 1024; }
+
+    int run_head(Workspace &ws, const float *g, int64_t B, float *logits, cudaStream_t st) override
+    {
+        float *f512 = ws.take<float>(B * 512);
+        float *f256 = ws.take<float>(B * 256);
+        IQ_CHECK(ws.ok(), "pointnet: workspace too small");
+        if (ws.dry) return 0;
+        if (int rc = dense(fc1, g, 1024, f512, B, ACT_RELU, st)) return rc;
+        if (int rc = dense(fc2, f512, 512, f256, B, ACT_RELU, st)) return rc;
+        return dense(fc3, f256, 256, logits, B, ACT_NONE, st);
+    }
+
+    int run_body(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *pooled,
+                 float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st) override
     {
         IQ_CHECK(N % 128 == 0, "pointnet: num_points must be a multiple of 128");
         const int64_t rows = Bc * N;
@@ -114,10 +127,7 @@ protected:
         }
         if (int rc = apply_transform(h64, t4096, 64, Bc, N, h64t, st)) return rc;
         if (int rc = dense(conv2, h64t, 64, a128, rows, ACT_RELU, st)) return rc;
-        if (int rc = dense_pool(conv3, a128, 128, Bc, N, ACT_NONE, pmax, parg, g1024, aux_crt, st)) return rc;
-        if (int rc = dense(fc1, g1024, 1024, f512, Bc, ACT_RELU, st)) return rc;
-        if (int rc = dense(fc2, f512, 512, f256, Bc, ACT_RELU, st)) return rc;
-        return dense(fc3, f256, 256, logits, Bc, ACT_NONE, st);
+        return dense_pool(conv3, a128, 128, Bc, N, ACT_NONE, pmax, parg, pooled, aux_crt, st);
     }
 };
 

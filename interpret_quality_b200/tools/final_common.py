@@ -12,7 +12,7 @@ import torch
 from .. import ops
 
 # permutations evaluated per internal pass of the fused engine; independent of args.shapley_batch_size
-ENGINE_PERMS_PER_PASS = 16
+ENGINE_PERMS_PER_PASS = 100
 
 
 def _device_of(model):
