@@ -139,6 +139,16 @@ int iq_topk_rows(const float *keys_dev, int64_t rows, int64_t N, int64_t ld, int
 int iq_linear(const float *x_dev, const float *w_dev, const float *b_dev, int64_t M, int64_t N, int64_t K, int act,
               int engine, float *y_dev, void *stream);
 
+/* conv1d(k=1) + BN + activation + global max / average pooling over the points of each cloud, the pattern of
+ * models/pointnet.py:35,83 and models/dgcnn.py:108-111: x (clouds*points, K), W (N,K) ->
+ * out_max (clouds,N), out_mean (clouds,N) or NULL, out_arg (clouds,N) i64 point index of the max or NULL. */
+int iq_linear_pool(const float *x_dev, const float *w_dev, const float *b_dev, int64_t clouds, int64_t points,
+                   int64_t N, int64_t K, int act, int engine, float *out_max_dev, float *out_mean_dev,
+                   int64_t *out_arg_dev, void *stream);
+
+/* GEMM engine of the masked forward: 1 = tcgen05 3xTF32 (default), 0 = exact fp32 SIMT. */
+int iq_model_set_engine(iq_model *m, int engine);
+
 #ifdef __cplusplus
 }
 #endif

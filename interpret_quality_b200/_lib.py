@@ -39,6 +39,8 @@ SIGNATURES = {
     "iq_knn_xyz": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "iq_topk_rows": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "iq_linear": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "iq_linear_pool": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp]),
+    "iq_model_set_engine": (_int, [_vp, _int]),
 }
 
 _lib = None

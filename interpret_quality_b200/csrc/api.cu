@@ -162,11 +162,73 @@ int iq_linear(const float *x, const float *w, const float *b, int64_t M, int64_t
               float *y, void *stream)
 {
     IQ_CHECK(x && w && y, "iq_linear: null pointer");
-    IQ_CHECK(engine == 0, "iq_linear: only the fp32 SIMT engine is built in");
+    if (engine == 1) {
+        // unit-test path: split the operands into scratch, then the tcgen05 kernel
+        float *buf = nullptr;
+        const size_t na = (size_t)M * K, nb = (size_t)N * K;
+        IQ_CUDA(cudaMalloc(&buf, sizeof(float) * 2 * (na + nb)));
+        cudaStream_t st = as_stream(stream);
+        int rc = launch_split_tf32(x, M, (int)K, K, buf, buf + na, K, st);
+        if (!rc) rc = launch_split_tf32(w, N, (int)K, K, buf + 2 * na, buf + 2 * na + nb, K, st);
+        TcGemm t;
+        t.A_hi = buf; t.A_lo = buf + na; t.lda = K; t.B_hi = buf + 2 * na; t.B_lo = buf + 2 * na + nb; t.ldb = K;
+        t.K = (int)K; t.M = (int)M; t.N = (int)N; t.C = y; t.ldc = N; t.bias = b; t.act = act;
+        if (!rc) rc = launch_gemm_tc(t, st);
+        cudaStreamSynchronize(st);
+        cudaFree(buf);
+        return rc;
+    }
+    IQ_CHECK(engine == 0, "iq_linear: unknown engine");
     GemmDesc g;
     g.A = x; g.lda = K; g.B = w; g.ldb = K; g.C = y; g.ldc = N;
     g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bias = b; g.act = act;
     return launch_sgemm(g, as_stream(stream));
+}
+
+int iq_linear_pool(const float *x, const float *w, const float *b, int64_t clouds, int64_t points, int64_t N, int64_t K,
+                   int act, int engine, float *out_max, float *out_mean, int64_t *out_arg, void *stream)
+{
+    IQ_CHECK(x && w && out_max, "iq_linear_pool: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const int64_t M = clouds * points;
+    if (engine == 1) {
+        float *buf = nullptr;
+        const size_t na = (size_t)M * K, nb = (size_t)N * K;
+        IQ_CUDA(cudaMalloc(&buf, sizeof(float) * 2 * (na + nb)));
+        int rc = launch_split_tf32(x, M, (int)K, K, buf, buf + na, K, st);
+        if (!rc) rc = launch_split_tf32(w, N, (int)K, K, buf + 2 * na, buf + 2 * na + nb, K, st);
+        TcGemm t;
+        t.mode = 1;
+        t.A_hi = buf + 2 * na; t.A_lo = buf + 2 * na + nb; t.lda = K; t.B_hi = buf; t.B_lo = buf + na; t.ldb = K;
+        t.K = (int)K; t.clouds = (int)clouds; t.points = (int)points; t.cout = (int)N;
+        t.out_max = out_max; t.out_mean = out_mean; t.out_arg = out_arg; t.ld_out = N; t.bias = b; t.act = act;
+        if (!rc) rc = launch_gemm_tc(t, st);
+        cudaStreamSynchronize(st);
+        cudaFree(buf);
+        return rc;
+    }
+    IQ_CHECK(engine == 0, "iq_linear_pool: unknown engine");
+    IQ_CHECK(points % 128 == 0, "iq_linear_pool: points must be a multiple of 128");
+    const int tiles = (int)(points / 128);
+    float *pm = nullptr;
+    IQ_CUDA(cudaMalloc(&pm, sizeof(float) * 3 * (size_t)clouds * tiles * N));
+    float *ps = pm + (size_t)clouds * tiles * N;
+    int32_t *pa = reinterpret_cast<int32_t *>(ps + (size_t)clouds * tiles * N);
+    GemmDesc g;
+    g.A = x; g.lda = K; g.B = w; g.ldb = K; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.bias = b; g.act = act;
+    g.pool_max = pm; g.pool_sum = ps; g.pool_arg = pa;
+    int rc = launch_sgemm(g, st);
+    if (!rc) rc = launch_pool_finish(pm, pa, ps, clouds, tiles, (int)points, (int)N, out_max, N, out_arg, out_mean, N, st);
+    cudaStreamSynchronize(st);
+    cudaFree(pm);
+    return rc;
+}
+
+int iq_model_set_engine(iq_model *m, int engine)
+{
+    IQ_CHECK(m && (engine == 0 || engine == 1), "iq_model_set_engine: bad argument");
+    m->impl->engine = engine;
+    return 0;
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@ namespace iq {
 namespace {
 
 struct EdgeLayer {
+    float *wcat_hi = nullptr, *wcat_lo = nullptr;   // tf32 split of wcat
     float *wcat = nullptr;       // (2*cout, cin): rows [0,cout) = s*Wa, rows [cout,2cout) = s*(Wb - Wa)
     float *bcat = nullptr;       // (2*cout): [0 ; t]
     int cin = 0, cout = 0, col = 0;
@@ -64,6 +65,9 @@ protected:
         float *feat = ws.take<float>(rows * 512);
         float *nxx = ws.take<float>(rows);
         float *pq = ws.take<float>(rows * 512);
+        const bool tc = engine == 1;
+        float *feat_hi = tc ? ws.take<float>(rows * 512) : nullptr;
+        float *feat_lo = tc ? ws.take<float>(rows * 512) : nullptr;
         float *dist = dynamic ? ws.take<float>(Bc * N * N) : nullptr;
         const int tiles = (int)(N / 128);
         float *pmax = ws.take<float>(Bc * tiles * 1024);
@@ -81,7 +85,15 @@ protected:
             const EdgeLayer &L = layers[l];
             const float *in = l == 0 ? pts : feat + layers[l - 1].col;
             const int64_t ldin = l == 0 ? 3 : 512;
-            if (l > 0 && dynamic) {
+            if (l > 0 && dynamic && tc) {
+                TcGemm d;
+                d.A_hi = feat_hi + layers[l - 1].col; d.A_lo = feat_lo + layers[l - 1].col; d.lda = 512;
+                d.B_hi = d.A_hi; d.B_lo = d.A_lo; d.ldb = 512;
+                d.K = L.cin; d.M = (int)rows; d.N = (int)N; d.rows_per_batch = (int)N;
+                d.C = dist; d.ldc = N; d.alpha = 2.0f; d.bias = nxx; d.tag = "tc_gram";
+                if (int rc = launch_gemm_tc(d, st)) return rc;
+                if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
+            } else if (l > 0 && dynamic) {
                 GemmDesc d;
                 d.A = in; d.lda = ldin; d.strideA = N * ldin;
                 d.B = in; d.ldb = ldin; d.strideB = N * ldin;
@@ -91,13 +103,33 @@ protected:
                 if (int rc = launch_sgemm(d, st)) return rc;
                 if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
             }
-            GemmDesc p;
-            p.A = in; p.lda = ldin; p.B = L.wcat; p.ldb = L.cin; p.C = pq; p.ldc = 2 * L.cout;
-            p.M = (int)rows; p.N = 2 * L.cout; p.K = L.cin; p.bias = L.bcat; p.tag = "sgemm_edge_pq";
-            if (int rc = launch_sgemm(p, st)) return rc;
+            if (l > 0 && tc) {
+                TcGemm p;
+                p.A_hi = feat_hi + layers[l - 1].col; p.A_lo = feat_lo + layers[l - 1].col; p.lda = 512;
+                p.B_hi = L.wcat_hi; p.B_lo = L.wcat_lo; p.ldb = L.cin;
+                p.K = L.cin; p.M = (int)rows; p.N = 2 * L.cout; p.C = pq; p.ldc = 2 * L.cout; p.bias = L.bcat;
+                p.tag = "tc_edge_pq";
+                if (int rc = launch_gemm_tc(p, st)) return rc;
+            } else {
+                GemmDesc p;
+                p.A = in; p.lda = ldin; p.B = L.wcat; p.ldb = L.cin; p.C = pq; p.ldc = 2 * L.cout;
+                p.M = (int)rows; p.N = 2 * L.cout; p.K = L.cin; p.bias = L.bcat; p.tag = "sgemm_edge_pq";
+                if (int rc = launch_sgemm(p, st)) return rc;
+            }
             if (int rc = launch_gather_max(pq, 2 * L.cout, idx, Bc, N, k, L.cout, ACT_LRELU, feat + L.col, 512,
-                                           (dynamic && l < 3) ? nxx : nullptr, st))
+                                           (dynamic && l < 3) ? nxx : nullptr, tc ? feat_hi + L.col : nullptr,
+                                           tc ? feat_lo + L.col : nullptr, st))
                 return rc;
+        }
+        if (tc) {
+            TcGemm c5;
+            c5.mode = 1;
+            c5.A_hi = conv5.w_hi; c5.A_lo = conv5.w_lo; c5.lda = 512;
+            c5.B_hi = feat_hi; c5.B_lo = feat_lo; c5.ldb = 512; c5.K = 512;
+            c5.clouds = (int)Bc; c5.points = (int)N; c5.cout = 1024;
+            c5.out_max = g; c5.out_mean = g + 1024; c5.ld_out = 2048; c5.bias = conv5.b; c5.act = ACT_LRELU;
+            c5.tag = "tc_conv5_pool";
+            return launch_gemm_tc(c5, st);
         }
         GemmDesc c5;
         c5.A = feat; c5.lda = 512; c5.B = conv5.w; c5.ldb = 512; c5.M = (int)rows; c5.N = 1024; c5.K = 512;
@@ -134,7 +166,13 @@ Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int
         for (int o = 0; o < cout[l]; ++o) bcat[cout[l] + o] = b[o];
         EdgeLayer &L = m->layers[l];
         L.cin = cin[l]; L.cout = cout[l]; L.col = col[l];
-        if (m->arena_.upload(wcat, &L.wcat) || m->arena_.upload(bcat, &L.bcat)) { err = last_error(); return nullptr; }
+        std::vector<float> whi, wlo;
+        split_tf32_host(wcat, whi, wlo);
+        if (m->arena_.upload(wcat, &L.wcat) || m->arena_.upload(bcat, &L.bcat) || m->arena_.upload(whi, &L.wcat_hi) ||
+            m->arena_.upload(wlo, &L.wcat_lo)) {
+            err = last_error();
+            return nullptr;
+        }
     }
     struct { Dense *d; const char *w; const char *b; const char *bn; int co, ci; } dense[4] = {
         {&m->conv5, "conv5.0.weight", "", "bn5", 1024, 512},
@@ -145,7 +183,13 @@ Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int
         std::vector<float> w, b;
         if (!fold_dense(sd, e.w, e.b, e.bn, e.co, e.ci, w, b, err)) return nullptr;
         e.d->cout = e.co; e.d->cin = e.ci;
-        if (m->arena_.upload(w, &e.d->w) || m->arena_.upload(b, &e.d->b)) { err = last_error(); return nullptr; }
+        std::vector<float> whi, wlo;
+        split_tf32_host(w, whi, wlo);
+        if (m->arena_.upload(w, &e.d->w) || m->arena_.upload(b, &e.d->b) || m->arena_.upload(whi, &e.d->w_hi) ||
+            m->arena_.upload(wlo, &e.d->w_lo)) {
+            err = last_error();
+            return nullptr;
+        }
     }
     return m.release();
 }

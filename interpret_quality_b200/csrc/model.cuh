@@ -36,8 +36,12 @@ struct Workspace {
 struct Dense {
     float *w = nullptr;
     float *b = nullptr;
+    float *w_hi = nullptr, *w_lo = nullptr;   // tf32 hi/lo split of w for the tcgen05 path
     int cout = 0, cin = 0;
 };
+
+// tf32 hi/lo split on the host (same rounding as split_tf32_kernel)
+void split_tf32_host(const std::vector<float> &w, std::vector<float> &hi, std::vector<float> &lo);
 
 struct DeviceArena {              // owns every device buffer of a model
     std::vector<void *> ptrs;
@@ -52,6 +56,8 @@ public:
     int num_classes = 10;
     // largest number of clouds one internal pass handles; forward() loops over chunks
     int chunk = 64;
+    // GEMM engine for the large products: 1 = tcgen05 3xTF32 (default), 0 = exact fp32 SIMT
+    int engine = 1;
     // bytes of workspace needed to run `B` clouds of `N` points (already capped by chunk)
     int64_t workspace_bytes(int64_t B, int64_t N);
     int forward(const float *x, int layout_point_major, int64_t B, int64_t N, float *logits, void *ws, int64_t ws_bytes,

@@ -1,5 +1,6 @@
 // Shared model plumbing: error state, device arena, BN folding, chunked forward.
 #include <math.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -115,6 +116,24 @@ bool fold_dense(const StateDict &sd, const std::string &w_key, const std::string
         b[o] = (float)(s * (bias ? (double)bias[o] : 0.0) + t);
     }
     return true;
+}
+
+void split_tf32_host(const std::vector<float> &w, std::vector<float> &hi, std::vector<float> &lo)
+{
+    auto rnd = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xffffe000u;
+        float r;
+        memcpy(&r, &u, 4);
+        return r;
+    };
+    hi.resize(w.size());
+    lo.resize(w.size());
+    for (size_t i = 0; i < w.size(); ++i) {
+        hi[i] = rnd(w[i]);
+        lo[i] = rnd(w[i] - hi[i]);
+    }
 }
 
 int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,

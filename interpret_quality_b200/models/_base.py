@@ -101,6 +101,12 @@ class IQModule(nn.Module):
         except Exception:
             pass
 
+    def set_engine(self, engine):
+        """GEMM engine of the forward pass: "3xtf32" (tcgen05, default) or "fp32" (exact SIMT)."""
+        code = {"3xtf32": 1, "tc": 1, "fp32": 0, "simt": 0}[engine]
+        _lib.check(_lib.load().iq_model_set_engine(self._get_handle(), code))
+        self._ws = None
+
     def set_chunk(self, chunk):
         """Clouds per internal pass (tuning knob; results do not depend on it)."""
         _lib.check(_lib.load().iq_model_set_chunk(self._get_handle(), int(chunk)))

@@ -170,3 +170,19 @@ def linear(x, w, b=None, act=0, engine=0):
     bp = _chk(b, torch.float32, "b").data_ptr() if b is not None else 0
     _lib.check(_lib.load().iq_linear(x.data_ptr(), w.data_ptr(), bp, M, N, K, act, engine, y.data_ptr(), _stream()))
     return y
+
+
+def linear_pool(x, w, b, clouds, points, act=0, engine=0, want_mean=True, want_arg=False):
+    """Pooled 1x1 conv: x (clouds*points, K), w (N,K) -> (max (clouds,N), mean | None, argmax | None)."""
+    _chk(x, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    K = x.shape[1]
+    N = w.shape[0]
+    mx = torch.empty((clouds, N), dtype=torch.float32, device=x.device)
+    mean = torch.empty((clouds, N), dtype=torch.float32, device=x.device) if want_mean else None
+    arg = torch.empty((clouds, N), dtype=torch.int64, device=x.device) if want_arg else None
+    bp = _chk(b, torch.float32, "b").data_ptr() if b is not None else 0
+    _lib.check(_lib.load().iq_linear_pool(x.data_ptr(), w.data_ptr(), bp, clouds, points, N, K, act, engine,
+                                          mx.data_ptr(), mean.data_ptr() if want_mean else 0,
+                                          arg.data_ptr() if want_arg else 0, _stream()))
+    return mx, mean, arg

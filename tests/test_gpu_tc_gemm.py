@@ -1,0 +1,84 @@
+"""Unit parity of the tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu) against float64 torch and the exact fp32 SIMT GEMM."""
+import numpy as np
+import pytest
+import torch
+
+from interpret_quality_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 64), (256, 128, 128), (1024, 256, 64), (4096, 512, 128),
+                                   (2048, 1024, 512), (128 * 149, 128, 96)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_store_epilogue_vs_float64(M, N, K, act):
+    rs = np.random.RandomState(M + N + K)
+    x = (rs.normal(size=(M, K)) * rs.uniform(0.1, 4.0, size=(1, K))).astype(np.float32)
+    w = rs.normal(size=(N, K)).astype(np.float32)
+    b = rs.normal(size=(N,)).astype(np.float32)
+    want = torch.from_numpy(x).double() @ torch.from_numpy(w).double().T + torch.from_numpy(b).double()
+    if act == 2:
+        want = torch.nn.functional.leaky_relu(want, 0.2)
+    want = want.numpy()
+    got_tc = ops.linear(cu(x), cu(w), cu(b), act=act, engine=1).cpu().numpy()
+    got_fp32 = ops.linear(cu(x), cu(w), cu(b), act=act, engine=0).cpu().numpy()
+    scale = np.abs(want).max()
+    e_tc, e_fp32 = np.abs(got_tc - want).max() / scale, np.abs(got_fp32 - want).max() / scale
+    assert e_fp32 <= 2e-6
+    assert e_tc <= 4e-6, (e_tc, e_fp32)            # 3xTF32 sits at fp32 noise; single-pass TF32 would be ~5e-4
+
+
+def test_single_pass_tf32_would_fail_this_bar():
+    """Sanity of the bar above: rounding the operands to TF32 once is two orders of magnitude worse."""
+    rs = np.random.RandomState(0)
+    x = rs.normal(size=(256, 128)).astype(np.float32)
+    w = rs.normal(size=(128, 128)).astype(np.float32)
+    rnd = lambda a: ((a.view(np.uint32) + 0x1000) & 0xffffe000).view(np.float32)
+    want = x.astype(np.float64) @ w.astype(np.float64).T
+    tf32 = rnd(x.copy()).astype(np.float64) @ rnd(w.copy()).astype(np.float64).T
+    assert np.abs(tf32 - want).max() / np.abs(want).max() > 1e-4
+
+
+@pytest.mark.parametrize("clouds,points,N,K", [(1, 128, 128, 32), (3, 1024, 1024, 512), (5, 2048, 256, 128),
+                                               (160, 1024, 128, 64)])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_pool_epilogue_vs_float64(clouds, points, N, K, engine):
+    rs = np.random.RandomState(clouds + points + N + K)
+    x = rs.normal(size=(clouds * points, K)).astype(np.float32)
+    x[points // 2:points // 2 + 40] = x[0]                       # duplicated points -> argmax ties
+    w = rs.normal(size=(N, K)).astype(np.float32)
+    b = rs.normal(size=(N,)).astype(np.float32)
+    y = torch.nn.functional.leaky_relu(torch.from_numpy(x).double() @ torch.from_numpy(w).double().T
+                                       + torch.from_numpy(b).double(), 0.2).view(clouds, points, N)
+    mx, mean, arg = ops.linear_pool(cu(x), cu(w), cu(b), clouds, points, act=2, engine=engine, want_arg=True)
+    scale = float(y.abs().max())
+    assert np.abs(mx.cpu().numpy() - y.max(1)[0].numpy()).max() / scale <= 4e-6
+    assert np.abs(mean.cpu().numpy() - y.mean(1).numpy()).max() / scale <= 4e-6
+    # the reported arg-max point reaches the max value (ties / fp32 noise may move the index itself)
+    picked = torch.gather(y, 1, arg.cpu().view(clouds, 1, N)).squeeze(1).numpy()
+    assert np.abs(picked - y.max(1)[0].numpy()).max() / scale <= 4e-6
+    assert int(arg.min()) >= 0 and int(arg.max()) < points
+
+
+def test_batched_gram_keys_through_dgcnn_engine_switch():
+    """Same DGCNN forward through both engines: logits agree to fp32 noise, so the kNN graphs agree."""
+    import types
+    from interpret_quality_b200 import synthetic
+    from interpret_quality_b200.tools import final_util
+    from oracle import coalition, geom
+    a = types.SimpleNamespace(model="dgcnn", k=20, dataset="shapenet", device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict("dgcnn"))
+    data = synthetic.make_cloud(1024)
+    rid = geom.region_id(data[0], geom.fps(data, 32)[0])
+    masked = geom.mask_shapley(data[0], coalition.center_of(data), synthetic.make_orders(2, 32), rid)
+    x = cu(masked)
+    model.set_engine("3xtf32")
+    tc = model.forward_point_major(x).cpu().numpy()
+    model.set_engine("fp32")
+    fp = model.forward_point_major(x).cpu().numpy()
+    assert np.abs(tc - fp).max() / np.abs(fp).max() <= 5e-5
