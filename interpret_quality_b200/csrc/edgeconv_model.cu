@@ -85,7 +85,12 @@ protected:
             const EdgeLayer &L = layers[l];
             const float *in = l == 0 ? pts : feat + layers[l - 1].col;
             const int64_t ldin = l == 0 ? 3 : 512;
-            if (l > 0 && dynamic && tc) {
+            // Anything upstream of a dynamic kNN stays on the exact fp32 engine: a masked region is hundreds of
+            // coincident points whose identical kNN rows flip together, so key noise above fp32 level shows up
+            // as 1e-3-sized jumps in the logits ("precision policy").  Downstream-only products
+            // (last EdgeConv, conv5) and the whole static-graph GCNN run on tcgen05 3xTF32.
+            const bool tc_keys = false;
+            if (l > 0 && dynamic && tc && tc_keys) {
                 TcGemm d;
                 d.A_hi = feat_hi + layers[l - 1].col; d.A_lo = feat_lo + layers[l - 1].col; d.lda = 512;
                 d.B_hi = d.A_hi; d.B_lo = d.A_lo; d.ldb = 512;
@@ -103,7 +108,7 @@ protected:
                 if (int rc = launch_sgemm(d, st)) return rc;
                 if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
             }
-            if (l > 0 && tc) {
+            if (l > 0 && tc && (!dynamic || l == 3)) {
                 TcGemm p;
                 p.A_hi = feat_hi + layers[l - 1].col; p.A_lo = feat_lo + layers[l - 1].col; p.lda = 512;
                 p.B_hi = L.wcat_hi; p.B_lo = L.wcat_lo; p.ldb = L.cin;
