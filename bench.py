@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "gcnn", "pointnet"])
+    ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "gcnn", "pointnet", "pointnet2", "pointconv"])
     ap.add_argument("--points", type=int, default=1024)
     ap.add_argument("--perms", type=int, default=100, help="permutations per step (NUM_SAMPLES of the reference)")
     ap.add_argument("--chunk", type=int, default=0, help="clouds per internal pass (0 = library default)")
@@ -58,7 +58,8 @@ def peaks():
 
 def config_of(a, n_gpus):
     return {"workload": "%s_k20_shapley_%dperm_x33clouds_N%d_R32" % (a.model, a.perms, a.points),
-            "model_class": {"dgcnn": "DGCNN_cls", "gcnn": "GCNN_cls", "pointnet": "PointNetCls"}[a.model],
+            "model_class": {"dgcnn": "DGCNN_cls", "gcnn": "GCNN_cls", "pointnet": "PointNetCls", "pointnet2": "PointNet2ClsMsg",
+                            "pointconv": "PointConvDensityClsSsg"}[a.model],
             "num_points": a.points, "num_regions": R, "permutations_per_step_per_gpu": a.perms,
             "forwards_per_step_per_gpu": a.perms * (R + 1), "parallelism": "perm-shard x%d" % n_gpus,
             "l2_policy": "256 MiB buffer rewritten between timed steps (flush); per-step working set also exceeds L2",

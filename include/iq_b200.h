@@ -126,6 +126,12 @@ int iq_model_forward(iq_model *m, const float *x_dev, int point_major, int64_t B
 
 /* ---- building blocks of the forward pass, exported for unit tests ---------------------------- */
 
+/* query_ball_point(radius, nsample, xyz, new_xyz): models/pointnet2.py:70-91 (copy: models/pointconv.py:80-100).
+ * xyz (B,N,3), new_xyz (B,S,3) -> idx (B,S,nsample) i32: first nsample indices in index order with d^2 <= r^2
+ * (fp32 compare against float(radius^2)), padded with the first hit. */
+int iq_ball_query(const float *xyz_dev, const float *new_xyz_dev, int64_t B, int64_t N, int64_t S, double radius,
+                  int nsample, int32_t *idx_dev, void *stream);
+
 /* knn(x, k) for 3-d input: models/dgcnn.py:12-18.  xyz (B,N,3) point-major -> idx (B,N,k) i32, the k
  * largest of -|xj|^2 + 2 xi.xj - |xi|^2 per row, unordered, lowest index on ties at the boundary. */
 int iq_knn_xyz(const float *xyz_dev, int64_t B, int64_t N, int k, int32_t *idx_dev, void *stream);

@@ -112,6 +112,7 @@ iq_model *iq_model_create(const char *kind, int n_tensors, const char *const *na
     if (kd == "dgcnn") impl = create_edgeconv_model(sd, true, k, num_classes, err);
     else if (kd == "gcnn" || kd == "gcnn_adv") impl = create_edgeconv_model(sd, false, k, num_classes, err);
     else if (kd == "pointnet") impl = create_pointnet_model(sd, num_classes, err);
+    else if (kd == "pointnet2") impl = create_pointnet2_model(sd, num_classes, err);
     else err = "unknown model kind '" + kd + "'";
     if (!impl) {
         set_error("iq_model_create: " + err);
@@ -144,6 +145,13 @@ int iq_model_forward(iq_model *m, const float *x, int point_major, int64_t B, in
 {
     IQ_CHECK(m, "iq_model_forward: null model");
     return m->impl->forward(x, point_major, B, N, logits, ws, ws_bytes, trans_feat, crt_points, as_stream(stream));
+}
+
+int iq_ball_query(const float *xyz, const float *new_xyz, int64_t B, int64_t N, int64_t S, double radius, int nsample,
+                  int32_t *idx, void *stream)
+{
+    IQ_CHECK(xyz && new_xyz && idx, "iq_ball_query: null pointer");
+    return launch_ball_query(xyz, new_xyz, B, N, S, radius, nsample, idx, as_stream(stream));
 }
 
 int iq_knn_xyz(const float *xyz, int64_t B, int64_t N, int k, int32_t *idx, void *stream)

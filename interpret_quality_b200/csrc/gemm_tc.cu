@@ -154,20 +154,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 }
 
+__device__ __forceinline__ float tf32_round(float x)
+{
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 struct TcParams {
     int K;                       // multiple of 32
     int mode;                    // 0 = STORE, 1 = POOL
     // STORE: units = (M/128) * (Ncols/BN), one accumulator tile each
     int n_tiles;                 // Ncols / BN
     int rows_per_batch;          // > 0: B rows live in the same batch as the A rows (Gram), else B is shared
-    // POOL: units = clouds * (Cout/128); tiles_per_unit = points / BN
-    int m_tiles;                 // Cout / 128
-    int points;                  // points per cloud
+    // POOL: columns are grouped in runs of `points` consecutive B rows (points of a cloud / neighbours of a centroid).
+    //   points >= BN: units = groups * m_tiles, tiles_per_unit = points / BN (running reduction across tiles)
+    //   points <  BN: units = column tiles * m_tiles, BN / points groups reduced inside one tile
+    int m_tiles;                 // ceil(Cout / 128)
+    int points;                  // columns per group
     int num_units, tiles_per_unit;
     float alpha;
     const float *bias;           // STORE: per column (index b_row0 + c), POOL: per row (channel)
     int act;
-    float *C;                    // STORE output
+    float *C;                    // STORE outputs: fp32 and / or its tf32 hi/lo split (same leading dimension)
+    float *C_hi, *C_lo;
     int64_t ldc;
     float *out_max;              // POOL outputs, (clouds, ld_out)
     float *out_mean;
@@ -185,6 +193,8 @@ struct TcSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
 };
 
+constexpr int tmem_cols_for(int bn) { return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512; }
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
@@ -201,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = p.K / TBK;
+    const int kblocks = (p.K + TBK - 1) / TBK;          // TMA zero-fills the K tail
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_ahi); prefetch_tmap(&map_alo); prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
@@ -210,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, 2 * BN);
+        tmem_alloc(tmem_ptr, tmem_cols_for(BN));
         tmem_relinquish();
     }
     tc_fence_before();
@@ -224,9 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             a_row0 = mt * TBM;
             b_row0 = nt * BN + (p.rows_per_batch > 0 ? (a_row0 / p.rows_per_batch) * p.rows_per_batch : 0);
         } else {
-            const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
+            const int grp = unit / p.m_tiles, mt = unit - grp * p.m_tiles;
             a_row0 = mt * TBM;
-            b_row0 = cloud * p.points + j * BN;
+            b_row0 = p.points >= BN ? grp * p.points + j * BN : grp * BN;
         }
     };
 
@@ -300,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
                 if (p.mode == 0) {
                     const int nt = unit % p.n_tiles;
-                    float *crow = p.C + (int64_t)(a_row0 + row_in_tile) * p.ldc + (int64_t)nt * BN;
+                    const int64_t coff = (int64_t)(a_row0 + row_in_tile) * p.ldc + (int64_t)nt * BN;
 #pragma unroll 1
                     for (int c0 = 0; c0 < BN; c0 += 32) {
                         float v[32];
@@ -310,21 +320,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                             const float b = p.bias ? __ldg(p.bias + b_row0 + c0 + i) : 0.0f;
                             v[i] = apply_act(fmaf(p.alpha, v[i], b), p.act);
                         }
+                        if (p.C) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4 *>(crow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            for (int i = 0; i < 32; i += 4)
+                                *reinterpret_cast<float4 *>(p.C + coff + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
+                        if (p.C_hi) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float h[4], l[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) { h[q] = tf32_round(v[i + q]); l[q] = tf32_round(v[i + q] - h[q]); }
+                                *reinterpret_cast<float4 *>(p.C_hi + coff + c0 + i) = make_float4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<float4 *>(p.C_lo + coff + c0 + i) = make_float4(l[0], l[1], l[2], l[3]);
+                            }
+                        }
                     }
                 } else {
-                    const float b = p.bias ? __ldg(p.bias + a_row0 + row_in_tile) : 0.0f;
+                    const int ch = a_row0 + row_in_tile;
+                    const float b = (p.bias && ch < p.cout) ? __ldg(p.bias + ch) : 0.0f;
+                    const int grp0 = unit / p.m_tiles;
 #pragma unroll 1
                     for (int c0 = 0; c0 < BN; c0 += 32) {
                         float v[32];
                         tmem_ld32(taddr + c0, v);
+                        if (p.points >= BN) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float y = apply_act(fmaf(p.alpha, v[i], b), p.act);
-                            if (y > run_max) { run_max = y; run_arg = j * BN + c0 + i; }
-                            run_sum += y;
+                            for (int i = 0; i < 32; ++i) {
+                                const float y = apply_act(fmaf(p.alpha, v[i], b), p.act);
+                                if (y > run_max) { run_max = y; run_arg = j * BN + c0 + i; }
+                                run_sum += y;
+                            }
+                        } else {                                            // several groups inside this tile
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float y = apply_act(fmaf(p.alpha, v[i], b), p.act);
+                                run_max = fmaxf(run_max, y);
+                                if (((c0 + i + 1) & (p.points - 1)) == 0) {              // points is a power of two here
+                                    const int64_t g = (int64_t)grp0 * (BN / p.points) + (c0 + i) / p.points;
+                                    if (ch < p.cout) p.out_max[g * p.ld_out + ch] = run_max;
+                                    run_max = -INFINITY;
+                                }
+                            }
                         }
                     }
                 }
@@ -333,12 +370,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (p.mode == 1) {
-                const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
+            if (p.mode == 1 && p.points >= BN) {
+                const int grp = unit / p.m_tiles, mt = unit - grp * p.m_tiles;
                 const int ch = mt * TBM + row_in_tile;
-                p.out_max[(int64_t)cloud * p.ld_out + ch] = run_max;
-                if (p.out_mean) p.out_mean[(int64_t)cloud * p.ld_out + ch] = run_sum / (float)p.points;
-                if (p.out_arg) p.out_arg[(int64_t)cloud * p.cout + ch] = run_arg;
+                if (ch < p.cout) {
+                    p.out_max[(int64_t)grp * p.ld_out + ch] = run_max;
+                    if (p.out_mean) p.out_mean[(int64_t)grp * p.ld_out + ch] = run_sum / (float)p.points;
+                    if (p.out_arg) p.out_arg[(int64_t)grp * p.cout + ch] = run_arg;
+                }
             }
         }
     }
@@ -347,15 +386,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, tmem_cols_for(BN));
     }
 }
 
 // ------------------------------------------------------------------ hi/lo split
-__device__ __forceinline__ float tf32_round(float x)
-{
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
 
 __global__ void split_tf32_kernel(const float *__restrict__ x, int64_t rows, int cols, int64_t ldx,
                                   float *__restrict__ hi, float *__restrict__ lo, int64_t ldo)
@@ -436,37 +471,26 @@ int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float
     return 0;
 }
 
-bool tc_gemm_supported(const TcGemm &g)
+static int pick_bn(int n)
 {
-    if (g.K % TBK != 0 || g.K < TBK) return false;
-    if (g.mode == 0) return g.M % TBM == 0 && g.N % 128 == 0;
-    return g.cout % TBM == 0 && g.points % 128 == 0 && g.clouds >= 1;
+    for (int bn : {128, 96, 64, 32})
+        if (n % bn == 0) return bn;
+    return 0;
 }
 
-int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
+bool tc_gemm_supported(const TcGemm &g)
 {
-    ProfileScope _ps(g.tag, st);
-    IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape (M % 128, N % 128, K % 32 must be 0)");
-    constexpr int BN = 128, STAGES = 3;
+    if (g.K < 4 || g.K % 4 != 0) return false;
+    if (g.mode == 0) return g.M % TBM == 0 && pick_bn(g.N) != 0;
+    if (g.cout < 1 || g.points < 1 || g.clouds < 1) return false;
+    if (g.points >= 128) return g.points % 128 == 0;
+    return 128 % g.points == 0 && ((int64_t)g.clouds * g.points) % 128 == 0;
+}
+
+template <int BN, int STAGES>
+static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_t b_rows, cudaStream_t st)
+{
     using S = TcSmem<BN, STAGES>;
-    TcParams p = {};
-    p.K = g.K; p.mode = g.mode; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
-    int64_t a_rows, b_rows;
-    if (g.mode == 0) {
-        p.n_tiles = g.N / BN; p.rows_per_batch = g.rows_per_batch; p.C = g.C; p.ldc = g.ldc;
-        p.num_units = (g.M / TBM) * p.n_tiles; p.tiles_per_unit = 1;
-        a_rows = g.M;
-        b_rows = g.rows_per_batch > 0 ? g.M : g.N;
-        IQ_CHECK(g.C && g.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0, "gemm_tc: C must be 16-byte aligned");
-    } else {
-        p.m_tiles = g.cout / TBM; p.points = g.points; p.cout = g.cout;
-        p.num_units = g.clouds * p.m_tiles; p.tiles_per_unit = g.points / BN;
-        p.out_max = g.out_max; p.out_mean = g.out_mean; p.out_arg = g.out_arg; p.ld_out = g.ld_out;
-        a_rows = g.cout;
-        b_rows = (int64_t)g.clouds * g.points;
-        IQ_CHECK(g.out_max, "gemm_tc: pooling output missing");
-    }
-    if (p.num_units == 0) return 0;
     CUtensorMap mahi, malo, mbhi, mblo;
     if (int rc = make_map(&mahi, g.A_hi, a_rows, g.K, g.lda, TBM)) return rc;
     if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
@@ -482,6 +506,42 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
+}
+
+int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
+{
+    ProfileScope _ps(g.tag, st);
+    IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape");
+    TcParams p = {};
+    p.K = g.K; p.mode = g.mode; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
+    int64_t a_rows, b_rows;
+    int bn;
+    if (g.mode == 0) {
+        bn = pick_bn(g.N);
+        p.n_tiles = g.N / bn; p.rows_per_batch = g.rows_per_batch; p.C = g.C; p.C_hi = g.C_hi; p.C_lo = g.C_lo;
+        p.ldc = g.ldc;
+        p.num_units = (g.M / TBM) * p.n_tiles; p.tiles_per_unit = 1;
+        a_rows = g.M;
+        b_rows = g.rows_per_batch > 0 ? g.M : g.N;
+        IQ_CHECK((g.C || (g.C_hi && g.C_lo)) && g.ldc % 4 == 0, "gemm_tc: no output or misaligned leading dimension");
+    } else {
+        bn = 128;
+        p.m_tiles = (g.cout + TBM - 1) / TBM; p.points = g.points; p.cout = g.cout;
+        b_rows = (int64_t)g.clouds * g.points;
+        if (g.points >= bn) { p.num_units = g.clouds * p.m_tiles; p.tiles_per_unit = g.points / bn; }
+        else { p.num_units = (int)(b_rows / bn) * p.m_tiles; p.tiles_per_unit = 1; }
+        p.out_max = g.out_max; p.out_mean = g.out_mean; p.out_arg = g.out_arg; p.ld_out = g.ld_out;
+        a_rows = g.cout;
+        IQ_CHECK(g.out_max, "gemm_tc: pooling output missing");
+        IQ_CHECK(g.points >= bn || (!g.out_mean && !g.out_arg), "gemm_tc: mean / argmax need groups of >= 128 columns");
+    }
+    if (p.num_units == 0) return 0;
+    switch (bn) {
+    case 128: return launch_tc_variant<128, 3>(g, p, a_rows, b_rows, st);
+    case 96: return launch_tc_variant<96, 3>(g, p, a_rows, b_rows, st);
+    case 64: return launch_tc_variant<64, 4>(g, p, a_rows, b_rows, st);
+    default: return launch_tc_variant<32, 4>(g, p, a_rows, b_rows, st);
+    }
 }
 
 }  // namespace iq

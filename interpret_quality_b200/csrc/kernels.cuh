@@ -60,9 +60,11 @@ struct TcGemm {
     // STORE
     int M = 0, N = 0;             // A rows, output columns
     int rows_per_batch = 0;       // > 0: batched Gram, B rows taken from the batch the A rows belong to
-    float *C = nullptr;
+    float *C = nullptr;           // fp32 output and / or its tf32 hi/lo split (for a tcgen05 consumer)
+    float *C_hi = nullptr, *C_lo = nullptr;
     int64_t ldc = 0;
-    // POOL: A = weights (cout, K), B = activations (clouds * points, K); reduces over the points of each cloud
+    // POOL: A = weights (cout, K), B = activations (clouds * points, K); reduces over each run of `points`
+    // consecutive rows of B (points of a cloud, or the neighbours of one centroid)
     int clouds = 0, points = 0, cout = 0;
     float *out_max = nullptr, *out_mean = nullptr;
     int64_t *out_arg = nullptr;
@@ -86,5 +88,15 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
                       int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,
                       cudaStream_t st);
 int launch_xyz_to_point_major(const float *x_cf, int64_t B, int64_t N, float *x_pm, cudaStream_t st);
+
+// grouping.cu
+int launch_ball_query(const float *xyz, const float *new_xyz, int64_t B, int64_t N, int64_t S, double radius, int K,
+                      int32_t *idx, cudaStream_t st);
+int launch_group_sub_act(const float *U, int64_t ldu, const float *V, int64_t ldv, const float *bias,
+                         const int32_t *idx, int64_t B, int S, int K, int Nsrc, int C, int act, float *out,
+                         float *out_hi, float *out_lo, int64_t ldo, cudaStream_t st);
+int launch_group_max(const float *in, int64_t ld, int64_t groups, int K, int C, float *out, int64_t ldo, cudaStream_t st);
+int launch_copy_cols(const float *src, int64_t lds, int64_t rows, int cols, float *dst, int64_t ldd, int pad_to,
+                     cudaStream_t st);
 
 }  // namespace iq

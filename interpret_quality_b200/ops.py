@@ -186,3 +186,15 @@ def linear_pool(x, w, b, clouds, points, act=0, engine=0, want_mean=True, want_a
                                           mx.data_ptr(), mean.data_ptr() if want_mean else 0,
                                           arg.data_ptr() if want_arg else 0, _stream()))
     return mx, mean, arg
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    """xyz (B,N,3), new_xyz (B,S,3) -> (B,S,nsample) int32 (models/pointnet2.py:70-91)."""
+    _chk(xyz, torch.float32, "xyz")
+    _chk(new_xyz, torch.float32, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty((B, S, nsample), dtype=torch.int32, device=xyz.device)
+    _lib.check(_lib.load().iq_ball_query(xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, float(radius), nsample,
+                                         out.data_ptr(), _stream()))
+    return out

@@ -74,6 +74,16 @@ def test_square_distance_bit_exact(geo):
     assert np.array_equal(sq, geom.square_distance3(new_xyz, clouds))
 
 
+def test_ball_query_bit_exact(geo):
+    clouds = _masked_clouds(geo)
+    f1 = geo["fps512"].astype(np.int64)
+    new_xyz = np.take_along_axis(clouds, f1[:, :, None].repeat(3, 2), 1)
+    for radius, K in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        got = ops.ball_query(radius, K, cu(clouds), cu(new_xyz)).cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, geo["ball_r%d" % int(radius * 10)].astype(np.int64)), radius
+        assert np.array_equal(got, geom.ball_query(radius, K, clouds, new_xyz))
+
+
 def test_shapley_mask_bit_exact_fused_and_in_place(geo):
     data = synthetic.make_cloud(1024)
     center = coalition.center_of(data)

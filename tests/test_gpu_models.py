@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 R, LBL, TOL = 32, 3, 1e-3
 DEV = "cuda:0"
 # models whose forward pass is implemented in libiq_b200.so
-MODELS = ["pointnet", "dgcnn", "gcnn"]
+MODELS = ["pointnet", "dgcnn", "gcnn", "pointnet2"]
 
 
 def relmax(a, b):
@@ -173,3 +173,17 @@ def test_error_vs_float64_oracle_is_fp32_noise(name):
     got = model(x.to(DEV))
     got = got[0] if isinstance(got, tuple) else got
     assert relmax(got.cpu().numpy(), want) <= 5e-5
+
+
+@pytest.mark.parametrize("name", ["gcnn", "pointnet2"])
+def test_fp32_engine_agrees_with_tcgen05_engine(name):
+    model, a = make(name)
+    data = synthetic.make_cloud(1024)
+    rid = geom.region_id(data[0], geom.fps(data, R)[0])
+    masked = geom.mask_shapley(data[0], coalition.center_of(data), synthetic.make_orders(1, R), rid)[::3]
+    x = torch.from_numpy(masked).to(DEV)
+    model.set_engine("3xtf32")
+    tc = model.forward_point_major(x).cpu().numpy()
+    model.set_engine("fp32")
+    fp = model.forward_point_major(x).cpu().numpy()
+    assert relmax(tc, fp) <= 5e-5
