@@ -113,6 +113,7 @@ iq_model *iq_model_create(const char *kind, int n_tensors, const char *const *na
     else if (kd == "gcnn" || kd == "gcnn_adv") impl = create_edgeconv_model(sd, false, k, num_classes, err);
     else if (kd == "pointnet") impl = create_pointnet_model(sd, num_classes, err);
     else if (kd == "pointnet2") impl = create_pointnet2_model(sd, num_classes, err);
+    else if (kd == "pointconv") impl = create_pointconv_model(sd, num_classes, err);
     else err = "unknown model kind '" + kd + "'";
     if (!impl) {
         set_error("iq_model_create: " + err);

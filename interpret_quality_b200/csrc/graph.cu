@@ -158,6 +158,46 @@ knn_xyz_kernel(const float *__restrict__ xyz, int point_major, int N, int k, int
     }
 }
 
+// ---- knn_point (models/pointconv.py:103-114): K nearest source points of every centroid, exact
+// square_distance(new_xyz, xyz) recipe, torch.topk(largest=False, sorted=False)
+template <int V>
+__global__ void __launch_bounds__(256)
+knn_point_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, int N, int S, int k,
+                 int32_t *__restrict__ idx)
+{
+    extern __shared__ float4 pts[];
+    __shared__ float scratch[8][TOPK_SCRATCH];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (int64_t)b * N * 3;
+    for (int i = tid; i < N; i += 256) {
+        const float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+        pts[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    }
+    __syncthreads();
+    for (int s = blockIdx.x * 64 + warp; s < min(S, (int)(blockIdx.x + 1) * 64); s += 8) {
+        const float *c = new_xyz + ((int64_t)b * S + s) * 3;
+        const float cx = c[0], cy = c[1], cz = c[2];
+        const float cc = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+        float key[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int j = v * 32 + lane;
+            if (j < N) {
+                const float4 q = pts[j];
+                float dot = __fmul_rn(cx, q.x);
+                dot = __fmaf_rn(cy, q.y, dot);
+                dot = __fmaf_rn(cz, q.z, dot);
+                float t = __fmul_rn(-2.0f, dot);
+                t = __fadd_rn(t, cc);
+                key[v] = -__fadd_rn(t, q.w);
+            } else {
+                key[v] = -INFINITY;
+            }
+        }
+        warp_topk<V>(key, k, lane, idx + ((int64_t)b * S + s) * k, scratch[warp]);
+    }
+}
+
 // ---- top-k over rows of a key matrix already in memory (feature-space kNN, knn_point)
 template <int V>
 __global__ void __launch_bounds__(256)
@@ -294,6 +334,24 @@ int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int 
     return dispatch_v(N, [&](auto v) {
         constexpr int V = decltype(v)::value;
         knn_xyz_kernel<V><<<grid, 256, smem, st>>>(xyz, point_major, (int)N, k, rows_per_cta, idx);
+        IQ_COUNT_LAUNCH();
+        IQ_LAUNCH_CHECK();
+        return 0;
+    });
+}
+
+int launch_knn_point(const float *xyz, const float *new_xyz, int64_t B, int64_t N, int64_t S, int k, int32_t *idx,
+                     cudaStream_t st)
+{
+    ProfileScope _ps("knn_point", st);
+    IQ_CHECK(N >= 1 && N <= 2048, "knn_point: num_points must be in [1,2048]");
+    IQ_CHECK(k >= 1 && k <= N && B <= 65535, "knn_point: bad k or batch");
+    if (B * S == 0) return 0;
+    dim3 grid((unsigned)ceil_div(S, 64), (unsigned)B);
+    const size_t smem = sizeof(float4) * (size_t)N;
+    return dispatch_v(N, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        knn_point_kernel<V><<<grid, 256, smem, st>>>(xyz, new_xyz, (int)N, (int)S, k, idx);
         IQ_COUNT_LAUNCH();
         IQ_LAUNCH_CHECK();
         return 0;

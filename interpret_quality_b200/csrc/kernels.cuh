@@ -81,6 +81,8 @@ int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float
 
 // graph.cu
 int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int k, int32_t *idx, cudaStream_t st);
+int launch_knn_point(const float *xyz, const float *new_xyz, int64_t B, int64_t N, int64_t S, int k, int32_t *idx,
+                     cudaStream_t st);
 int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx,
                      cudaStream_t st);
 int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st);

@@ -80,6 +80,7 @@ protected:
 Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int num_classes, std::string &err);
 Model *create_pointnet_model(const StateDict &sd, int num_classes, std::string &err);
 Model *create_pointnet2_model(const StateDict &sd, int num_classes, std::string &err);
+Model *create_pointconv_model(const StateDict &sd, int num_classes, std::string &err);
 
 // host-side folding helpers (models_common.cu)
 bool fold_dense(const StateDict &sd, const std::string &w_key, const std::string &b_key, const std::string &bn_prefix,

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 R, LBL, TOL = 32, 3, 1e-3
 DEV = "cuda:0"
 # models whose forward pass is implemented in libiq_b200.so
-MODELS = ["pointnet", "dgcnn", "gcnn", "pointnet2"]
+MODELS = ["pointnet", "dgcnn", "gcnn", "pointnet2", "pointconv"]
 
 
 def relmax(a, b):
@@ -175,7 +175,7 @@ def test_error_vs_float64_oracle_is_fp32_noise(name):
     assert relmax(got.cpu().numpy(), want) <= 5e-5
 
 
-@pytest.mark.parametrize("name", ["gcnn", "pointnet2"])
+@pytest.mark.parametrize("name", ["gcnn", "pointnet2", "pointconv"])
 def test_fp32_engine_agrees_with_tcgen05_engine(name):
     model, a = make(name)
     data = synthetic.make_cloud(1024)
