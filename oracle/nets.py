@@ -160,7 +160,8 @@ def pointnet2_msg(x, sd):
 
 # --------------------------------------------------------------------------- PointConv
 def _sqdist3(a, b):
-    return torch.from_numpy(geom.square_distance3(a.contiguous().numpy(), b.contiguous().numpy()))
+    # geometry is always evaluated in fp32 (the reference's dtype); cast back for the float64 yardstick runs
+    return torch.from_numpy(geom.square_distance3(a.contiguous().numpy(), b.contiguous().numpy())).to(a.dtype)
 
 
 def _pointconv_sa(xyz, feats, sd, p, npoint, nsample, bandwidth, group_all):
