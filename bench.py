@@ -170,24 +170,36 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def kernel_work(a):
-    """Algorithmic work per forward (one masked cloud) of every kernel family, for the roofline leg.
-    FLOPs are 2*MAC of the product the kernel evaluates; bytes are compulsory traffic."""
+    """Algorithmic work per forward (one masked cloud) of the kernel families, for the roofline leg.
+    "tensor": FLOPs = 2*MAC of the product the kernel evaluates (logical fp32 product; the tcgen05 kernels
+    execute 3 TF32 MMAs per logical MAC).  "hbm": compulsory bytes."""
     N, k = a.points, 20
-    w = {}
+    mac = lambda *terms: 2.0 * sum(r * ci * co for r, ci, co in terms)
+    w = {"mask_shapley": ("hbm", 12.0 * N), "reward": ("hbm", 44.0), "shapley_accumulate": ("hbm", 4.0 + 8.0 * R / (R + 1))}
     if a.model in ("dgcnn", "gcnn"):
-        w["sgemm_conv5_pool"] = ("tensor", 2.0 * N * 512 * 1024)
-        w["sgemm_edge_pq"] = ("tensor", 2.0 * N * (3 * 128 + 64 * 128 + 64 * 256 + 128 * 512))
+        w["tc_conv5_pool"] = w["sgemm_conv5_pool"] = ("tensor", mac((N, 512, 1024)))
         if a.model == "dgcnn":
-            w["sgemm_gram"] = ("tensor", 2.0 * N * N * (64 + 64 + 128))
+            w["sgemm_edge_pq"] = ("tensor", mac((N, 3, 128), (N, 64, 128), (N, 64, 256)))
+            w["tc_edge_pq"] = ("tensor", mac((N, 128, 512)))
+            w["sgemm_gram"] = w["tc_gram"] = ("tensor", mac((N, N, 64), (N, N, 64), (N, N, 128)))
             w["topk_rows"] = ("hbm", 3.0 * (4.0 * N * N + 4.0 * N * k))
-        w["gather_max"] = ("hbm", sum(4.0 * N * (2 * c + c) + 4.0 * N * k for c in (64, 64, 128, 256)))
+        else:
+            w["sgemm_edge_pq"] = ("tensor", mac((N, 3, 128)))
+            w["tc_edge_pq"] = ("tensor", mac((N, 64, 128), (N, 64, 256), (N, 128, 512)))
+        w["gather_max"] = ("hbm", sum(4.0 * N * (2 * c + 3 * c) + 4.0 * N * k for c in (64, 64, 128, 256)))
         w["knn_xyz"] = ("hbm", 12.0 * N + 4.0 * N * k)
-        w["sgemm_head"] = ("tensor", 2.0 * (2048 * 512 + 512 * 256 + 256 * 10))
-    else:
-        w["sgemm"] = ("tensor", 0.879e9)
-    w["mask_shapley"] = ("hbm", 12.0 * N)
-    w["reward"] = ("hbm", 44.0)
-    w["shapley_accumulate"] = ("hbm", 4.0 + 8.0 * R / (R + 1))
+    elif a.model == "pointnet":
+        w["tc_conv_pool"] = ("tensor", mac((N, 128, 1024)) * 3)
+        w["tc_conv"] = ("tensor", mac((N, 64, 128)) * 3 + mac((N, 64, 64)))
+    elif a.model == "pointnet2":
+        w["tc_sa_mlp2"] = ("tensor", mac((8192, 32, 32), (16384, 64, 64), (65536, 64, 96), (4096, 64, 64),
+                                         (8192, 128, 128), (16384, 128, 128)))
+        w["tc_sa_mlp3_pool"] = ("tensor", mac((8192, 32, 64), (16384, 64, 128), (65536, 96, 128), (4096, 64, 128),
+                                              (8192, 128, 256), (16384, 128, 256)))
+    elif a.model == "pointconv":
+        w["tc_sa_mlp2"] = ("tensor", mac((16384, 64, 64), (8192, 128, 128), (128, 256, 512)))
+        w["tc_sa_mlp3"] = ("tensor", mac((16384, 64, 128), (8192, 128, 256), (128, 512, 1024)))
+        w["tc_sa_linear"] = ("tensor", mac((512, 2048, 128), (128, 4096, 256)))
     return w
 
 

@@ -62,6 +62,7 @@ protected:
         const int64_t rows = Bc * N;
         float *xyz = ws.take<float>(rows * 3);
         int32_t *idx = ws.take<int32_t>(rows * k);
+        int32_t *cand = (dynamic && engine == 1) ? ws.take<int32_t>(rows * 32) : nullptr;
         float *feat = ws.take<float>(rows * 512);
         float *nxx = ws.take<float>(rows);
         float *pq = ws.take<float>(rows * 512);
@@ -85,11 +86,12 @@ protected:
             const EdgeLayer &L = layers[l];
             const float *in = l == 0 ? pts : feat + layers[l - 1].col;
             const int64_t ldin = l == 0 ? 3 : 512;
-            // Anything upstream of a dynamic kNN stays on the exact fp32 engine: a masked region is hundreds of
-            // coincident points whose identical kNN rows flip together, so key noise above fp32 level shows up
-            // as 1e-3-sized jumps in the logits ("precision policy").  Downstream-only products
-            // (last EdgeConv, conv5) and the whole static-graph GCNN run on tcgen05 3xTF32.
-            const bool tc_keys = false;
+            // A masked region is hundreds of coincident points whose identical kNN rows flip together, so noise in
+            // a dynamic-graph decision shows up as 1e-3-sized jumps of the logits ("precision policy").
+            // Features upstream of a dynamic kNN therefore stay on the exact fp32 engine, and the tcgen05 Gram keys
+            // only nominate 32 candidates per row; the k neighbours are decided by knn_rerank_kernel on directly
+            // evaluated distances.  Downstream-only products (last EdgeConv, conv5) and GCNN run on tcgen05 3xTF32.
+            const bool tc_keys = k <= 24 && N >= 32;
             if (l > 0 && dynamic && tc && tc_keys) {
                 TcGemm d;
                 d.A_hi = feat_hi + layers[l - 1].col; d.A_lo = feat_lo + layers[l - 1].col; d.lda = 512;
@@ -97,7 +99,8 @@ protected:
                 d.K = L.cin; d.M = (int)rows; d.N = (int)N; d.rows_per_batch = (int)N;
                 d.C = dist; d.ldc = N; d.alpha = 2.0f; d.bias = nxx; d.tag = "tc_gram";
                 if (int rc = launch_gemm_tc(d, st)) return rc;
-                if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
+                if (int rc = launch_topk_rows(dist, rows, N, N, 32, 1, cand, st)) return rc;
+                if (int rc = launch_knn_rerank(in, ldin, L.cin, cand, rows, N, k, idx, st)) return rc;
             } else if (l > 0 && dynamic) {
                 GemmDesc d;
                 d.A = in; d.lda = ldin; d.strideA = N * ldin;

@@ -34,55 +34,83 @@ __device__ __forceinline__ unsigned lanemask_lt()
     return m;
 }
 
-// k largest of the 32*V keys of a warp; lane l holds candidates j = v*32 + l.
-// Writes k candidate indices (unordered) to out[0..k).  scratch: TOPK_SCRATCH floats per warp.
+// ---- warp top-k ---------------------------------------------------------------------------------
+// k largest of the 32*V keys of a warp; lane l holds candidates j = v*32 + l.  Writes k candidate
+// indices (unordered) to out[0..k).  scratch: TOPK_SCRATCH floats per warp.
+//
+// Instruction budget matters (ncu: the first version spent ~1900 warp instructions per row, all in
+// ballot/popc chains), so membership is tracked in per-lane bit masks (bit v <=> key[v]), totals use
+// REDUX (__reduce_*_sync), positions come from one 5-step warp scan, and the ordered ballot walk is
+// only used to break ties at the boundary by lowest index.
+template <int V> struct LaneMask { typedef uint32_t type; };
+template <> struct LaneMask<64> { typedef uint64_t type; };
+__device__ __forceinline__ int mask_popc(uint32_t m) { return __popc(m); }
+__device__ __forceinline__ int mask_popc(uint64_t m) { return __popcll(m); }
+__device__ __forceinline__ int mask_ffs(uint32_t m) { return __ffs(m) - 1; }
+__device__ __forceinline__ int mask_ffs(uint64_t m) { return __ffsll((long long)m) - 1; }
+
+__device__ __forceinline__ int warp_exclusive_scan(int x, int lane)
+{
+    int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    return incl - x;
+}
+
+// value of rank `r` (0 = largest) among the 32 per-lane values `u` (ordered-uint keys), by REDUX extraction
+// from whichever end is closer
+__device__ __forceinline__ uint32_t warp_select_rank(uint32_t u, int r, int lane)
+{
+    uint32_t res = 0;
+    if (r < 16) {
+        for (int it = 0; it <= r; ++it) {
+            res = __reduce_max_sync(FULL, u);
+            const unsigned b = __ballot_sync(FULL, u == res);
+            if (lane == __ffs(b) - 1) u = 0u;                       // remove one instance (0 is below every real key)
+        }
+    } else {
+        for (int it = 0; it <= 31 - r; ++it) {
+            res = __reduce_min_sync(FULL, u);
+            const unsigned b = __ballot_sync(FULL, u == res);
+            if (lane == __ffs(b) - 1) u = 0xffffffffu;
+        }
+    }
+    return res;
+}
+
 template <int V>
 __device__ __forceinline__ void warp_topk(const float (&key)[V], int k, int lane, int32_t *out, float *scratch)
 {
+    typedef typename LaneMask<V>::type mask_t;
     float T = 0.0f;
     bool have = false;
     if (k <= 32) {
         float m = key[0];
 #pragma unroll
         for (int v = 1; v < V; ++v) m = fmaxf(m, key[v]);
-        int r = 0;
+        // k-th largest lane maximum: at least k keys are >= T0
+        const float T0 = from_ordered_u32(warp_select_rank(ordered_u32(m), k - 1, lane));
+        mask_t mg = 0;
 #pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            const float o = __shfl_sync(FULL, m, s);
-            r += (o > m || (o == m && s < lane)) ? 1 : 0;
-        }
-        const unsigned bal = __ballot_sync(FULL, r == k - 1);
-        const float T0 = __shfl_sync(FULL, m, __ffs(bal) - 1);     // >= k keys are >= T0
-        int g = 0;
-#pragma unroll
-        for (int v = 0; v < V; ++v) g += key[v] > T0 ? 1 : 0;
+        for (int v = 0; v < V; ++v) mg |= (mask_t)(key[v] > T0 ? 1 : 0) << v;
+        const int g = mask_popc(mg);
         const int G = __reduce_add_sync(FULL, g);
         if (G < k) {
             T = T0;
             have = true;
-        } else if (G <= TOPK_SCRATCH) {
-            int base = 0;
+        } else if (G <= 32) {
+            // the k-th largest key is among the G keys above T0: one per lane, then rank select again
+            const int off = warp_exclusive_scan(g, lane);
+            int w = off;
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const bool pred = key[v] > T0;
-                const unsigned b = __ballot_sync(FULL, pred);
-                if (pred) scratch[base + __popc(b & lanemask_lt())] = key[v];
-                base += __popc(b);
-            }
+            for (int v = 0; v < V; ++v)
+                if ((mg >> v) & 1) scratch[w++] = key[v];
             __syncwarp();
-            const float c0 = lane < G ? scratch[lane] : -INFINITY;
-            const float c1 = lane + 32 < G ? scratch[lane + 32] : -INFINITY;
-            int gt0 = 0, ge0 = 0, gt1 = 0, ge1 = 0;
-            for (int t = 0; t < G; ++t) {
-                const float x = scratch[t];
-                gt0 += x > c0; ge0 += x >= c0; gt1 += x > c1; ge1 += x >= c1;
-            }
-            const bool hit0 = lane < G && gt0 < k && ge0 >= k;
-            const bool hit1 = lane + 32 < G && gt1 < k && ge1 >= k;
-            const unsigned b0 = __ballot_sync(FULL, hit0), b1 = __ballot_sync(FULL, hit1);
-            const float t0 = __shfl_sync(FULL, c0, b0 ? __ffs(b0) - 1 : 0);
-            const float t1 = __shfl_sync(FULL, c1, b1 ? __ffs(b1) - 1 : 0);
-            T = b0 ? t0 : t1;
+            const uint32_t c = lane < G ? ordered_u32(scratch[lane]) : 0u;
+            T = from_ordered_u32(warp_select_rank(c, k - 1, lane));
             have = true;
             __syncwarp();
         }
@@ -98,23 +126,40 @@ __device__ __forceinline__ void warp_topk(const float (&key)[V], int k, int lane
         }
         T = from_ordered_u32(tu);
     }
-    int g2 = 0;
-#pragma unroll
-    for (int v = 0; v < V; ++v) g2 += key[v] > T ? 1 : 0;
-    const int G2 = __reduce_add_sync(FULL, g2);
-    const int need = k - G2;
-    int base_gt = 0, base_eq = 0;
+    // ---- emission: everything above T, then the lowest-index keys equal to T
+    mask_t mgt = 0, meq = 0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const bool gt = key[v] > T, eq = key[v] == T;
-        const unsigned bgt = __ballot_sync(FULL, gt), beq = __ballot_sync(FULL, eq);
-        if (gt) out[base_gt + __popc(bgt & lanemask_lt())] = v * 32 + lane;
-        if (eq) {
-            const int slot = base_eq + __popc(beq & lanemask_lt());
-            if (slot < need) out[G2 + slot] = v * 32 + lane;
+        mgt |= (mask_t)(key[v] > T ? 1 : 0) << v;
+        meq |= (mask_t)(key[v] == T ? 1 : 0) << v;
+    }
+    const int cgt = mask_popc(mgt), ceq = mask_popc(meq);
+    const int G2 = __reduce_add_sync(FULL, cgt);
+    const int E = __reduce_add_sync(FULL, ceq);
+    const int need = k - G2;
+    int w = warp_exclusive_scan(cgt, lane);
+    while (mgt) {
+        const int v = mask_ffs(mgt);
+        mgt &= mgt - 1;
+        out[w++] = v * 32 + lane;
+    }
+    if (E == need) {                                               // no tie at the boundary: take them all
+        w = G2 + warp_exclusive_scan(ceq, lane);
+        while (meq) {
+            const int v = mask_ffs(meq);
+            meq &= meq - 1;
+            out[w++] = v * 32 + lane;
         }
-        base_gt += __popc(bgt);
-        base_eq += __popc(beq);
+    } else {                                                       // ties: first `need` in index order (v major, lane minor)
+        int base = 0;
+#pragma unroll 1
+        for (int v = 0; v < V && base < need; ++v) {
+            const bool eq = (meq >> v) & 1;
+            const unsigned b = __ballot_sync(FULL, eq);
+            const int slot = base + __popc(b & lanemask_lt());
+            if (eq && slot < need) out[G2 + slot] = v * 32 + lane;
+            base += __popc(b);
+        }
     }
 }
 
@@ -217,6 +262,39 @@ topk_rows_kernel(const float *__restrict__ keys, int64_t rows, int N, int64_t ld
         key[v] = j < N ? (largest ? x : -x) : -INFINITY;
     }
     warp_topk<V>(key, k, lane, idx + row * k, scratch[warp]);
+}
+
+// ---- exact re-rank of kNN candidates --------------------------------------------------------------
+// The tcgen05 Gram keys only nominate 32 candidates per row; the final k neighbours are decided here on
+// squared distances evaluated directly, sum_c (x_i[c] - x_j[c])^2, fp32 differences accumulated in float64,
+// i.e. without the cancellation of the expanded form -|x_i|^2 + 2 x_i.x_j - |x_j|^2 the reference evaluates in
+// fp32 (models/dgcnn.py:13-15).  Ties (coincident points) go to the lower point index.  One warp per row,
+// lane = candidate; output sorted by (distance, index).
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const float *__restrict__ x, int64_t ld, int C, const int32_t *__restrict__ cand, int64_t rows,
+                  int N, int k, int32_t *__restrict__ idx)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int64_t cloud0 = (row / N) * N;
+    const int j = cand[row * 32 + lane];
+    const float4 *xi = reinterpret_cast<const float4 *>(x + row * ld);
+    const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
+    double acc = 0.0;
+    for (int c = 0; c < (C >> 2); ++c) {
+        const float4 a = __ldg(xi + c), b = __ldg(xj + c);
+        const double d0 = (double)(a.x - b.x), d1 = (double)(a.y - b.y), d2 = (double)(a.z - b.z), d3 = (double)(a.w - b.w);
+        acc = fma(d0, d0, acc); acc = fma(d1, d1, acc); acc = fma(d2, d2, acc); acc = fma(d3, d3, acc);
+    }
+    int rank = 0;
+#pragma unroll 8
+    for (int s = 0; s < 32; ++s) {
+        const double o = __shfl_sync(FULL, acc, s);
+        const int oj = __shfl_sync(FULL, j, s);
+        rank += (o < acc || (o == acc && oj < j)) ? 1 : 0;
+    }
+    if (rank < k) idx[row * k + rank] = j;
 }
 
 __global__ void sqnorm_rows_kernel(const float *__restrict__ x, int64_t rows, int C, int64_t ld, float *__restrict__ out)
@@ -373,6 +451,18 @@ int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int
         IQ_LAUNCH_CHECK();
         return 0;
     });
+}
+
+int launch_knn_rerank(const float *x, int64_t ld, int C, const int32_t *cand, int64_t rows, int64_t N, int k,
+                      int32_t *idx, cudaStream_t st)
+{
+    ProfileScope _ps("knn_rerank", st);
+    IQ_CHECK(C % 4 == 0 && ld % 4 == 0 && k <= 32 && N >= 32, "knn_rerank: bad shape");
+    if (rows == 0) return 0;
+    knn_rerank_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(x, ld, C, cand, rows, (int)N, k, idx);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st)

@@ -30,6 +30,7 @@ struct GemmDesc {
     const float *A = nullptr;      // (M,K) row-major, leading dimension lda
     const float *B = nullptr;      // (N,K) row-major, leading dimension ldb   ->  C = A * B^T
     float *C = nullptr;            // (M,N) row-major, leading dimension ldc (may be null in pool mode)
+    float *C_hi = nullptr, *C_lo = nullptr;   // optional tf32 hi/lo split of the output (same ldc) for a tcgen05 consumer
     int64_t lda = 0, ldb = 0, ldc = 0;
     int64_t strideA = 0, strideB = 0, strideC = 0, strideBias = 0;   // per batch element
     int M = 0, N = 0, K = 0, batch = 1;
@@ -85,6 +86,8 @@ int launch_knn_point(const float *xyz, const float *new_xyz, int64_t B, int64_t 
                      cudaStream_t st);
 int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx,
                      cudaStream_t st);
+int launch_knn_rerank(const float *x, int64_t ld, int C, const int32_t *cand, int64_t rows, int64_t N, int k,
+                      int32_t *idx, cudaStream_t st);
 int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st);
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
                       int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,

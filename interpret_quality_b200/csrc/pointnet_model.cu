@@ -37,12 +37,34 @@ public:
     const char *kind() const override { return "pointnet"; }
 
 protected:
-    static int dense(const Dense &d, const float *in, int64_t ldin, float *out, int64_t M, int act, cudaStream_t st)
+    static int dense(const Dense &d, const float *in, int64_t ldin, float *out, int64_t M, int act, cudaStream_t st,
+                     float *out_hi = nullptr, float *out_lo = nullptr)
     {
         GemmDesc g;
-        g.A = in; g.lda = ldin; g.B = d.w; g.ldb = d.cin; g.C = out; g.ldc = d.cout;
+        g.A = in; g.lda = ldin; g.B = d.w; g.ldb = d.cin; g.C = out; g.C_hi = out_hi; g.C_lo = out_lo; g.ldc = d.cout;
         g.M = (int)M; g.N = d.cout; g.K = d.cin; g.bias = d.b; g.act = act;
         return launch_sgemm(g, st);
+    }
+    // tcgen05: (rows, cin) hi/lo -> act(x W^T + b) as hi/lo (rows, cout)
+    static int dense_tc(const Dense &d, const float *in_hi, const float *in_lo, float *out_hi, float *out_lo, int64_t M,
+                        int act, cudaStream_t st)
+    {
+        TcGemm t;
+        t.A_hi = in_hi; t.A_lo = in_lo; t.lda = d.cin; t.B_hi = d.w_hi; t.B_lo = d.w_lo; t.ldb = d.cin; t.K = d.cin;
+        t.M = (int)M; t.N = d.cout; t.C_hi = out_hi; t.C_lo = out_lo; t.ldc = d.cout; t.bias = d.b; t.act = act;
+        t.tag = "tc_conv";
+        return launch_gemm_tc(t, st);
+    }
+    // tcgen05: conv + BN + act + max over the points of each cloud (+ argmax)
+    static int dense_pool_tc(const Dense &d, const float *in_hi, const float *in_lo, int64_t Bc, int64_t N, int act,
+                             float *out, int64_t *out_arg, cudaStream_t st)
+    {
+        TcGemm t;
+        t.mode = 1;
+        t.A_hi = d.w_hi; t.A_lo = d.w_lo; t.lda = d.cin; t.B_hi = in_hi; t.B_lo = in_lo; t.ldb = d.cin; t.K = d.cin;
+        t.clouds = (int)Bc; t.points = (int)N; t.cout = d.cout; t.out_max = out; t.out_arg = out_arg; t.ld_out = d.cout;
+        t.bias = d.b; t.act = act; t.tag = "tc_conv_pool";
+        return launch_gemm_tc(t, st);
     }
     static int dense_pool(const Dense &d, const float *in, int64_t ldin, int64_t Bc, int64_t N, int act, float *pmax,
                           int32_t *parg, float *out, int64_t *out_arg, cudaStream_t st)
@@ -55,24 +77,34 @@ protected:
                                   0, st);
     }
     // T-Net: in (rows, k) -> tmat (Bc, k*k) holding the transposed transform
-    int run_tnet(const TNet &t, const float *in, int64_t ldin, int64_t Bc, int64_t N, float *a64, float *a128,
-                 float *pmax, float *g1024, float *f512, float *f256, float *tmat, cudaStream_t st)
+    // in: fp32 rows (SIMT first layer when in_hi == nullptr) or a tf32 hi/lo pair
+    int run_tnet(const TNet &t, const float *in, const float *in_hi, const float *in_lo, int64_t ldin, int64_t Bc,
+                 int64_t N, float *a64, float *a64lo, float *a128, float *a128lo, float *pmax, float *g1024, float *f512,
+                 float *f256, float *tmat, cudaStream_t st)
     {
         const int64_t rows = Bc * N;
-        if (int rc = dense(t.c1, in, ldin, a64, rows, ACT_RELU, st)) return rc;
-        if (int rc = dense(t.c2, a64, 64, a128, rows, ACT_RELU, st)) return rc;
-        if (int rc = dense_pool(t.c3, a128, 128, Bc, N, ACT_RELU, pmax, nullptr, g1024, nullptr, st)) return rc;
+        if (engine == 1) {
+            if (in_hi) { if (int rc = dense_tc(t.c1, in_hi, in_lo, a64, a64lo, rows, ACT_RELU, st)) return rc; }
+            else { if (int rc = dense(t.c1, in, ldin, nullptr, rows, ACT_RELU, st, a64, a64lo)) return rc; }
+            if (int rc = dense_tc(t.c2, a64, a64lo, a128, a128lo, rows, ACT_RELU, st)) return rc;
+            if (int rc = dense_pool_tc(t.c3, a128, a128lo, Bc, N, ACT_RELU, g1024, nullptr, st)) return rc;
+        } else {
+            if (int rc = dense(t.c1, in, ldin, a64, rows, ACT_RELU, st)) return rc;
+            if (int rc = dense(t.c2, a64, 64, a128, rows, ACT_RELU, st)) return rc;
+            if (int rc = dense_pool(t.c3, a128, 128, Bc, N, ACT_RELU, pmax, nullptr, g1024, nullptr, st)) return rc;
+        }
         if (int rc = dense(t.f1, g1024, 1024, f512, Bc, ACT_RELU, st)) return rc;
         if (int rc = dense(t.f2, f512, 512, f256, Bc, ACT_RELU, st)) return rc;
         return dense(t.f3, f256, 256, tmat, Bc, ACT_NONE, st);
     }
     // out[b] (N, k) = in[b] (N, k) * T[b], with tmat[b] = T[b]^T stored (k, k) row-major
     static int apply_transform(const float *in, const float *tmat, int k, int64_t Bc, int64_t N, float *out,
-                               cudaStream_t st)
+                               cudaStream_t st, float *out_hi = nullptr, float *out_lo = nullptr)
     {
         GemmDesc g;
         g.A = in; g.lda = k; g.strideA = N * k; g.B = tmat; g.ldb = k; g.strideB = (int64_t)k * k;
-        g.C = out; g.ldc = k; g.strideC = N * k; g.M = (int)N; g.N = k; g.K = k; g.batch = (int)Bc;
+        g.C = out; g.C_hi = out_hi; g.C_lo = out_lo; g.ldc = k; g.strideC = N * k; g.M = (int)N; g.N = k; g.K = k;
+        g.batch = (int)Bc; g.tag = "sgemm_transform";
         return launch_sgemm(g, st);
     }
 
@@ -101,6 +133,11 @@ protected:
         float *a128 = ws.take<float>(rows * 128);
         float *h64 = ws.take<float>(rows * 64);
         float *h64t = ws.take<float>(rows * 64);
+        const bool tc = engine == 1;
+        float *a64lo = tc ? ws.take<float>(rows * 64) : nullptr;
+        float *a128lo = tc ? ws.take<float>(rows * 128) : nullptr;
+        float *h64hi = tc ? ws.take<float>(rows * 64) : nullptr;
+        float *h64lo = tc ? ws.take<float>(rows * 64) : nullptr;
         float *pmax = ws.take<float>(Bc * tiles * 1024);
         int32_t *parg = ws.take<int32_t>(Bc * tiles * 1024);
         float *g1024 = ws.take<float>(Bc * 1024);
@@ -116,14 +153,22 @@ protected:
             if (int rc = launch_xyz_to_point_major(x, Bc, N, xyz, st)) return rc;
             pts = xyz;
         }
-        if (int rc = run_tnet(stn, pts, 3, Bc, N, a64, a128, pmax, g1024, f512, f256, t9, st)) return rc;
+        if (int rc = run_tnet(stn, pts, nullptr, nullptr, 3, Bc, N, a64, a64lo, a128, a128lo, pmax, g1024, f512, f256, t9, st))
+            return rc;
         if (int rc = apply_transform(pts, t9, 3, Bc, N, xt, st)) return rc;
-        if (int rc = dense(conv1, xt, 3, h64, rows, ACT_RELU, st)) return rc;
-        if (int rc = run_tnet(fstn, h64, 64, Bc, N, a64, a128, pmax, g1024, f512, f256, t4096, st)) return rc;
+        if (int rc = dense(conv1, xt, 3, h64, rows, ACT_RELU, st, h64hi, h64lo)) return rc;
+        if (int rc = run_tnet(fstn, h64, h64hi, h64lo, 64, Bc, N, a64, a64lo, a128, a128lo, pmax, g1024, f512, f256, t4096, st))
+            return rc;
         if (aux_trans_feat) {
             transpose_square_kernel<<<(unsigned)Bc, 256, 0, st>>>(t4096, 64, aux_trans_feat);
             IQ_COUNT_LAUNCH();
             IQ_LAUNCH_CHECK();
+        }
+        if (tc) {
+            // the point transform writes its output already split; conv2 / conv3 run on tcgen05
+            if (int rc = apply_transform(h64, t4096, 64, Bc, N, nullptr, st, h64t, a64lo)) return rc;
+            if (int rc = dense_tc(conv2, h64t, a64lo, a128, a128lo, rows, ACT_RELU, st)) return rc;
+            return dense_pool_tc(conv3, a128, a128lo, Bc, N, ACT_NONE, pooled, aux_crt, st);
         }
         if (int rc = apply_transform(h64, t4096, 64, Bc, N, h64t, st)) return rc;
         if (int rc = dense(conv2, h64t, 64, a128, rows, ACT_RELU, st)) return rc;
@@ -150,7 +195,13 @@ bool make_dense(PointNetModel *m, const StateDict &sd, const std::string &conv, 
         b.swap(b2);
     }
     d.cout = co; d.cin = ci;
-    if (m->arena_.upload(w, &d.w) || m->arena_.upload(b, &d.b)) { err = last_error(); return false; }
+    std::vector<float> hi, lo;
+    split_tf32_host(w, hi, lo);
+    if (m->arena_.upload(w, &d.w) || m->arena_.upload(b, &d.b) || m->arena_.upload(hi, &d.w_hi) ||
+        m->arena_.upload(lo, &d.w_lo)) {
+        err = last_error();
+        return false;
+    }
     return true;
 }
 

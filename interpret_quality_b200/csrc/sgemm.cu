@@ -150,6 +150,24 @@ sgemm_kernel(const GemmDesc g)
         }
     }
 
+    if (g.C_hi) {
+        float *Ch = g.C_hi + (int64_t)bz * g.strideC, *Cl = g.C_lo + (int64_t)bz * g.strideC;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (n >= g.N) continue;
+                const float h = __uint_as_float((__float_as_uint(acc[i][j]) + 0x1000u) & 0xffffe000u);
+                const float l = acc[i][j] - h;
+                Ch[(int64_t)m * g.ldc + n] = h;
+                Cl[(int64_t)m * g.ldc + n] = __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+            }
+        }
+    }
+
     if (g.pool_max) {
         // host guarantees M % 128 == 0, so every row of the tile is valid
         float cmax[8], csum[8];
@@ -223,7 +241,7 @@ int launch_sgemm(const GemmDesc &g, cudaStream_t st)
     ProfileScope _ps(g.tag, st);
     IQ_CHECK(g.M >= 0 && g.N >= 0 && g.K >= 1 && g.batch >= 1, "sgemm: bad shape");
     if (g.M == 0 || g.N == 0) return 0;
-    IQ_CHECK(g.C || g.pool_max, "sgemm: no output requested");
+    IQ_CHECK(g.C || g.C_hi || g.pool_max, "sgemm: no output requested");
     if (g.pool_max) IQ_CHECK(g.M % BM == 0, "sgemm: pooling epilogue needs M % 128 == 0");
     IQ_CHECK(g.batch <= 65535 && ceil_div(g.M, BM) <= 65535, "sgemm: grid too large");
     const bool vec = (g.K % 4 == 0) && (g.lda % 4 == 0) && (g.ldb % 4 == 0) && (g.strideA % 4 == 0) &&
