@@ -195,5 +195,25 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
+        elif n == "dgcnn_more":
+            pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
+
+
+def dgcnn_more():
+    """A wider DGCNN sample (12 more permutations = 396 masked clouds, logits only): the dynamic kNN makes
+    DGCNN the model whose parity is decided by near-tie neighbour choices, so it gets more coverage."""
+    model, margs = load_ref_model("dgcnn")
+    data, fps_idx, region_id = base_inputs(1024)
+    orders = synthetic.make_orders(16, R)[4:16]
+    args = types.SimpleNamespace(num_points=1024, num_regions=R, shapley_batch_size=4, num_samples=12,
+                                 softmax_type="modified", model="dgcnn", device=torch.device("cpu"))
+    with torch.no_grad():
+        phi, logits = ref_common.shap_sampling_all_regions_batch(model, data, torch.tensor([LBL]), region_id, orders, args)
+    np.savez_compressed(os.path.join(HERE, "dgcnn_more.npz"), shapley_phi=phi, shapley_logits=logits.numpy())
+    print("dgcnn_more.npz written", logits.shape)
+
+
+if __name__ == "__main__" and "dgcnn_more" in sys.argv[1:]:
+    dgcnn_more()

@@ -171,8 +171,14 @@ def test_error_vs_float64_oracle_is_fp32_noise(name):
     finally:
         torch.set_default_dtype(torch.float32)
     got = model(x.to(DEV))
-    got = got[0] if isinstance(got, tuple) else got
-    assert relmax(got.cpu().numpy(), want) <= 5e-5
+    got = (got[0] if isinstance(got, tuple) else got).cpu().numpy()
+    per_cloud = np.abs(got - want).max(1) / np.abs(want).max()
+    if name == "dgcnn":
+        # the dynamic kNN is discontinuous: fp32 vs float64 *features* can pick a different neighbour at a near tie
+        # (the reference's own fp32 run does); typical clouds must still sit at fp32 noise
+        assert np.median(per_cloud) <= 1e-5 and per_cloud.max() <= 1e-3
+    else:
+        assert per_cloud.max() <= 5e-5
 
 
 @pytest.mark.parametrize("name", ["gcnn", "pointnet2", "pointconv"])
@@ -187,3 +193,22 @@ def test_fp32_engine_agrees_with_tcgen05_engine(name):
     model.set_engine("fp32")
     fp = model.forward_point_major(x).cpu().numpy()
     assert relmax(tc, fp) <= 5e-5
+
+
+def test_dgcnn_wide_sample_vs_reference_golden(golden):
+    """528 masked clouds (16 permutations) against the reference's fp32 CPU logits.  The dynamic kNN makes single
+    clouds jump by a few 1e-4 when a near-tie neighbour is chosen differently (coincident masked points flip together);
+    the bar stays 1e-3 of scale for every cloud and almost all clouds must sit at fp32 noise."""
+    from interpret_quality_b200 import ops
+    model, a = make("dgcnn")
+    geo = golden("geometry")
+    ref = np.concatenate([golden("dgcnn")["shapley_logits"], golden("dgcnn_more")["shapley_logits"]], 0)
+    data = synthetic.make_cloud(1024)
+    masked = ops.mask_shapley(torch.from_numpy(data[0]).to(DEV), torch.from_numpy(np.asarray(geo["center"])).to(DEV),
+                              torch.from_numpy(synthetic.make_orders(16, R)).to(DEV),
+                              torch.from_numpy(geo["region_id_1024"]).to(DEV))
+    out = model.forward_point_major(masked).cpu().numpy()
+    err = np.abs(out - ref).max(1) / np.abs(ref).max()
+    assert err.max() <= TOL
+    assert np.median(err) <= 1e-5
+    assert (err > 1e-4).mean() <= 0.03
