@@ -161,6 +161,32 @@ int iq_knn_xyz(const float *xyz, int64_t B, int64_t N, int k, int32_t *idx, void
     return launch_knn_xyz(xyz, 1, B, N, k, idx, as_stream(stream));
 }
 
+int iq_knn_features(const float *x, int64_t B, int64_t N, int64_t C, int k, int32_t *idx, int32_t *cand_count,
+                    void *stream)
+{
+    IQ_CHECK(x && idx, "iq_knn_features: null pointer");
+    IQ_CHECK(knn_features_tc_supported(N, (int)C, k), "iq_knn_features: unsupported shape (N % 128, C in {64,128}, k <= 20)");
+    // unit-test path: scratch is allocated here; the model keeps all of it in its workspace
+    cudaStream_t st = as_stream(stream);
+    const int64_t rows = B * N;
+    if (rows == 0) return 0;
+    char *buf = nullptr;
+    const size_t nf = (size_t)rows * C;
+    const size_t bytes = sizeof(float) * (2 * nf + rows) + sizeof(uint16_t) * rows * KNN_CAND_CAP + sizeof(int32_t) * rows;
+    IQ_CUDA(cudaMalloc(&buf, bytes));
+    float *hi = reinterpret_cast<float *>(buf), *lo = hi + nf, *nxx = lo + nf;
+    int32_t *cnt = reinterpret_cast<int32_t *>(nxx + rows);
+    uint16_t *cand = reinterpret_cast<uint16_t *>(cnt + rows);
+    int rc = launch_split_tf32(x, rows, (int)C, C, hi, lo, C, st);
+    if (!rc) rc = launch_sqnorm_rows(x, rows, (int)C, C, nxx, st);
+    if (!rc) rc = launch_knn_features_tc(x, hi, lo, C, (int)C, nxx, B, N, k, cand, cnt, idx, st);
+    if (!rc && cand_count && cudaMemcpyAsync(cand_count, cnt, sizeof(int32_t) * rows, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = -2;
+    cudaStreamSynchronize(st);
+    cudaFree(buf);
+    return rc;
+}
+
 int iq_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx, void *stream)
 {
     IQ_CHECK(keys && idx, "iq_topk_rows: null pointer");

@@ -62,14 +62,17 @@ protected:
         const int64_t rows = Bc * N;
         float *xyz = ws.take<float>(rows * 3);
         int32_t *idx = ws.take<int32_t>(rows * k);
-        int32_t *cand = (dynamic && engine == 1) ? ws.take<int32_t>(rows * 32) : nullptr;
+        const bool tc = engine == 1;
+        // feature-space kNN fused on tcgen05 (knn_tc.cu): the N x N key matrix is never written
+        const bool tc_knn = dynamic && tc && knn_features_tc_supported(N, 64, k) && knn_features_tc_supported(N, 128, k);
+        uint16_t *cand = tc_knn ? ws.take<uint16_t>(rows * KNN_CAND_CAP) : nullptr;
+        int32_t *cnt = tc_knn ? ws.take<int32_t>(rows) : nullptr;
         float *feat = ws.take<float>(rows * 512);
         float *nxx = ws.take<float>(rows);
         float *pq = ws.take<float>(rows * 512);
-        const bool tc = engine == 1;
         float *feat_hi = tc ? ws.take<float>(rows * 512) : nullptr;
         float *feat_lo = tc ? ws.take<float>(rows * 512) : nullptr;
-        float *dist = dynamic ? ws.take<float>(Bc * N * N) : nullptr;
+        float *dist = (dynamic && !tc_knn) ? ws.take<float>(Bc * N * N) : nullptr;
         const int tiles = (int)(N / 128);
         float *pmax = ws.take<float>(Bc * tiles * 1024);
         float *psum = ws.take<float>(Bc * tiles * 1024);
@@ -89,18 +92,12 @@ protected:
             // A masked region is hundreds of coincident points whose identical kNN rows flip together, so noise in
             // a dynamic-graph decision shows up as 1e-3-sized jumps of the logits ("precision policy").
             // Features upstream of a dynamic kNN therefore stay on the exact fp32 engine, and the tcgen05 Gram keys
-            // only nominate 32 candidates per row; the k neighbours are decided by knn_rerank_kernel on directly
-            // evaluated distances.  Downstream-only products (last EdgeConv, conv5) and GCNN run on tcgen05 3xTF32.
-            const bool tc_keys = k <= 24 && N >= 32;
-            if (l > 0 && dynamic && tc && tc_keys) {
-                TcGemm d;
-                d.A_hi = feat_hi + layers[l - 1].col; d.A_lo = feat_lo + layers[l - 1].col; d.lda = 512;
-                d.B_hi = d.A_hi; d.B_lo = d.A_lo; d.ldb = 512;
-                d.K = L.cin; d.M = (int)rows; d.N = (int)N; d.rows_per_batch = (int)N;
-                d.C = dist; d.ldc = N; d.alpha = 2.0f; d.bias = nxx; d.tag = "tc_gram";
-                if (int rc = launch_gemm_tc(d, st)) return rc;
-                if (int rc = launch_topk_rows(dist, rows, N, N, 32, 1, cand, st)) return rc;
-                if (int rc = launch_knn_rerank(in, ldin, L.cin, cand, rows, N, k, idx, st)) return rc;
+            // only nominate candidates; the k neighbours are decided on directly evaluated distances (knn_tc.cu).
+            // Downstream-only products (last EdgeConv, conv5) and GCNN run on tcgen05 3xTF32.
+            if (l > 0 && tc_knn) {
+                if (int rc = launch_knn_features_tc(in, feat_hi + layers[l - 1].col, feat_lo + layers[l - 1].col, 512,
+                                                    L.cin, nxx, Bc, N, k, cand, cnt, idx, st))
+                    return rc;
             } else if (l > 0 && dynamic) {
                 GemmDesc d;
                 d.A = in; d.lda = ldin; d.strideA = N * ldin;

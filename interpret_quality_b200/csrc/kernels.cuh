@@ -80,6 +80,15 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st);
 int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float *hi, float *lo, int64_t ldo,
                       cudaStream_t st);
 
+// knn_tc.cu -- fused tcgen05 Gram + candidate selection + exact re-rank (feature-space kNN of DGCNN)
+constexpr int KNN_CAND_CAP = 64;      // candidate slots per row
+bool knn_features_tc_supported(int64_t N, int C, int k);
+// x (clouds*N, C) fp32 with leading dimension ld, x_hi / x_lo its tf32 split (same ld), nxx = -|x_j|^2 per row;
+// scratch: cand (rows, KNN_CAND_CAP) u16, cnt (rows) i32; out idx (rows, k) sorted by (distance, index)
+int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
+                           int64_t clouds, int64_t N, int k, uint16_t *cand, int32_t *cnt, int32_t *idx,
+                           cudaStream_t st);
+
 // graph.cu
 int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int k, int32_t *idx, cudaStream_t st);
 int launch_knn_point(const float *xyz, const float *new_xyz, int64_t B, int64_t N, int64_t S, int k, int32_t *idx,

@@ -151,6 +151,18 @@ def knn_xyz(xyz, k):
     return out
 
 
+def knn_features(x, k, return_counts=False):
+    """x (B,N,C) point-major features, C in {64,128} -> (B,N,k) int32 nearest points ordered by (distance, index):
+    the fused tcgen05 Gram + candidate selection + exact re-rank of csrc/knn_tc.cu (models/dgcnn.py:12-18)."""
+    _chk(x, torch.float32, "x")
+    B, N, C = x.shape
+    out = torch.empty((B, N, k), dtype=torch.int32, device=x.device)
+    cnt = torch.empty((B, N), dtype=torch.int32, device=x.device) if return_counts else None
+    _lib.check(_lib.load().iq_knn_features(x.data_ptr(), B, N, C, k, out.data_ptr(), cnt.data_ptr() if return_counts else None,
+                                           _stream()))
+    return (out, cnt) if return_counts else out
+
+
 def topk_rows(keys, k, largest=True):
     """keys (rows,N) -> (rows,k) int32, unordered exact top-k with lowest-index tie-breaking."""
     _chk(keys, torch.float32, "keys")
