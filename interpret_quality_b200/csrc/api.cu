@@ -172,11 +172,11 @@ int iq_knn_features(const float *x, int64_t B, int64_t N, int64_t C, int k, int3
     if (rows == 0) return 0;
     char *buf = nullptr;
     const size_t nf = (size_t)rows * C;
-    const size_t bytes = sizeof(float) * (2 * nf + rows) + sizeof(uint16_t) * rows * KNN_CAND_CAP + sizeof(int32_t) * rows;
+    const size_t bytes = sizeof(float) * (2 * nf + rows) + sizeof(uint32_t) * rows * 2 * (N / 32) + sizeof(int32_t) * rows;
     IQ_CUDA(cudaMalloc(&buf, bytes));
     float *hi = reinterpret_cast<float *>(buf), *lo = hi + nf, *nxx = lo + nf;
     int32_t *cnt = reinterpret_cast<int32_t *>(nxx + rows);
-    uint16_t *cand = reinterpret_cast<uint16_t *>(cnt + rows);
+    uint32_t *cand = reinterpret_cast<uint32_t *>(cnt + rows);
     int rc = launch_split_tf32(x, rows, (int)C, C, hi, lo, C, st);
     if (!rc) rc = launch_sqnorm_rows(x, rows, (int)C, C, nxx, st);
     if (!rc) rc = launch_knn_features_tc(x, hi, lo, C, (int)C, nxx, B, N, k, cand, cnt, idx, st);

@@ -65,7 +65,7 @@ protected:
         const bool tc = engine == 1;
         // feature-space kNN fused on tcgen05 (knn_tc.cu): the N x N key matrix is never written
         const bool tc_knn = dynamic && tc && knn_features_tc_supported(N, 64, k) && knn_features_tc_supported(N, 128, k);
-        uint16_t *cand = tc_knn ? ws.take<uint16_t>(rows * KNN_CAND_CAP) : nullptr;
+        uint32_t *cand = tc_knn ? ws.take<uint32_t>(rows * 2 * (N / 32)) : nullptr;
         int32_t *cnt = tc_knn ? ws.take<int32_t>(rows) : nullptr;
         float *feat = ws.take<float>(rows * 512);
         float *nxx = ws.take<float>(rows);

@@ -116,43 +116,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         }
     };
 
+    // Issuing warps: all 32 lanes walk the schedule in uniform control flow and one elected lane issues (tc_ptx.cuh,
+    // elect_one_sync) -- tcgen05.mma issue is paced by the tensor pipe, so every clock the issuer spends elsewhere is lost.
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
-                for (int j = 0; j < p.tiles_per_unit; ++j) {
-                    int a_row0, b_row0;
-                    tile_rows(unit, j, a_row0, b_row0);
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t *st = smem + stage * S::STAGE_BYTES;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
+            for (int j = 0; j < p.tiles_per_unit; ++j) {
+                int a_row0, b_row0;
+                tile_rows(unit, j, a_row0, b_row0);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * S::STAGE_BYTES;
+                    if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                         tma_load_2d(st, &map_ahi, &full_bar[stage], kb * TBK, a_row0);
                         tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * TBK, a_row0);
                         tma_load_2d(st + 2 * S::A_BYTES, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
                         tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_blo, &full_bar[stage], kb * TBK, b_row0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-        }
+            }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
-                for (int j = 0; j < p.tiles_per_unit; ++j) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        constexpr uint32_t idesc = make_idesc(BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
+            for (int j = 0; j < p.tiles_per_unit; ++j) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
-                        const uint64_t ahi = make_smem_desc(sbase), alo = make_smem_desc(sbase + S::A_BYTES);
-                        const uint64_t bhi = make_smem_desc(sbase + 2 * S::A_BYTES);
-                        const uint64_t blo = make_smem_desc(sbase + 2 * S::A_BYTES + S::B_BYTES);
+                    const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint64_t ahi = make_smem_desc(sbase), alo = make_smem_desc(sbase + S::A_BYTES);
+                    const uint64_t bhi = make_smem_desc(sbase + 2 * S::A_BYTES);
+                    const uint64_t blo = make_smem_desc(sbase + 2 * S::A_BYTES + S::B_BYTES);
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {            // small terms first
                             const uint64_t ad = term == 0 ? alo : ahi;
@@ -164,12 +167,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                             }
                         }
                         umma_commit(&empty_bar[stage]);                  // frees the stage when the MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (kb == kblocks - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
                     }
-                    umma_commit(&tmem_full[acc]);                        // accumulator complete
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-        }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
     } else {
         const int quad = warp & 3;                                       // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;

@@ -81,12 +81,12 @@ int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float
                       cudaStream_t st);
 
 // knn_tc.cu -- fused tcgen05 Gram + candidate selection + exact re-rank (feature-space kNN of DGCNN)
-constexpr int KNN_CAND_CAP = 64;      // candidate slots per row
+constexpr int KNN_CAND_CAP = 64;      // most candidates per row the re-rank handles
 bool knn_features_tc_supported(int64_t N, int C, int k);
 // x (clouds*N, C) fp32 with leading dimension ld, x_hi / x_lo its tf32 split (same ld), nxx = -|x_j|^2 per row;
-// scratch: cand (rows, KNN_CAND_CAP) u16, cnt (rows) i32; out idx (rows, k) sorted by (distance, index)
+// scratch: masks (rows, 2, N/32) u32, cnt (rows) i32; out idx (rows, k) sorted by (distance, index)
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
-                           int64_t clouds, int64_t N, int k, uint16_t *cand, int32_t *cnt, int32_t *idx,
+                           int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
                            cudaStream_t st);
 
 // graph.cu

@@ -5,24 +5,32 @@
 //
 // B200-first design: that N x N key matrix (134 MB per 32 clouds and layer) never leaves the SM.
 //
-//   gram_knn_kernel   persistent, one CTA per SM, unit = (cloud, 128-row tile of points i).
-//       warp 0      TMA producer.  The unit's A tile (128 x K, tf32 hi and lo) is loaded ONCE and stays resident
-//                   in shared memory; the cloud's points j stream through a ring of (BN x 32) hi/lo stages.
-//       warp 1      one lane issues tcgen05.mma.kind::tf32, 3xTF32 (Alo*Bhi + Ahi*Blo + Ahi*Bhi), accumulators
-//                   double buffered in TMEM.
-//       warps 2-5   epilogue, thread = row i.  Every unit sweeps the cloud's columns TWICE (recomputing the MMAs
-//                   is cheaper than holding 128 x N accumulators, which do not fit TMEM):
-//                     sweep 1  keys 2*G - |x_j|^2 folded into 64 running maxima (column j -> block j mod 64);
-//                              T0 = NOM-th largest block maximum (register bitonic network), so at least NOM
-//                              columns of the row have key >= T0;
-//                     sweep 2  every column with key > T0, and the first NOM with key == T0 (masked clouds are
-//                              full of coincident points, i.e. exact ties), is appended to the row's candidate
-//                              list: ~30 of 1024 columns.
-//   knn_rerank_list_kernel   the k neighbours are decided among the candidates on squared distances evaluated
+//   gram_knn_kernel   persistent, one CTA per SM, unit = (cloud, 128-row tile of points i), 320 threads.
+//       warp 0      TMA producer: the cloud's points j stream through a ring of (128 x 32) hi/lo stages.
+//       warp 1      one lane issues tcgen05.mma.kind::tf32, 3xTF32 (Alo*Bhi + Ahi*Blo + Ahi*Bhi).  The unit's A tile
+//                   (128 rows x K, tf32 hi and lo) is parked ONCE per unit in TMEM by the epilogue warps
+//                   (tcgen05.st, lane = row, column = k) and every MMA reads it from there: an SS-mode 128x128 tf32
+//                   MMA needs the whole 128 B/clk shared-memory read port for A and B, so with the TMA writes on
+//                   top the pipe starved (measured 45 % active); A-from-TMEM halves that traffic.  The remaining
+//                   TMEM columns hold 3 (K=64) or 2 (K=128) accumulator buffers.
+//       warps 2-9   epilogue.  Thread = (row i, column half): two warps share each TMEM lane quadrant and split the
+//                   columns of every tile (one warp per scheduler is latency bound: ncu showed ~0.2 IPC).
+//                   Every unit sweeps the cloud's columns TWICE (recomputing the MMAs is cheaper than holding
+//                   128 x N accumulators, which do not fit TMEM):
+//                     sweep 1  keys 2*G - |x_j|^2 folded into running maxima of strided column blocks
+//                              (column j -> block j mod 64); the two halves exchange their NOM largest block
+//                              maxima through shared memory and T0 = NOM-th largest of the union, so at least
+//                              NOM columns of the row have key >= T0;
+//                     sweep 2  branch-free: one bit per column for key > T0 and one for key == T0 (masked clouds
+//                              are full of coincident points, i.e. exact ties), written as (rows, 2, N/32) words.
+//   knn_rerank_mask_kernel   warp per row: decodes the masks (all columns above T0, then the lowest-index ties up to
+//                   NOM candidates: ~30 of 1024 columns) and decides the k neighbours on squared distances evaluated
 //                   directly, sum_c (x_i[c] - x_j[c])^2 with float64 accumulation -- without the cancellation of
 //                   the expanded form -- ties to the lower index; half-warp per candidate, coalesced row reads.
-//   knn_exact_rows_kernel    rows whose list overflowed (pathological column orders) or came up short are redone
-//                   exhaustively; normally no row takes this path.
+//   knn_exact_rows_kernel    rows whose candidate set overflowed (pathological column orders) or came up short are
+//                   redone exhaustively; normally no row takes this path.
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 #include "kernels.cuh"
 
@@ -32,7 +40,10 @@ using namespace tc;
 
 namespace {
 
-constexpr int KNN_THREADS = 192;
+constexpr int KNN_THREADS = 320;                // producer warp, MMA warp, 8 epilogue warps
+constexpr int KNN_EPI_THREADS = 256;
+constexpr int KNN_NOM = 24;                     // columns nominated per row (>= k + slack for 3xTF32 key noise)
+constexpr int XCH_STRIDE = KNN_NOM + 1;         // padded row of the threshold exchange (bank-conflict free)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct KnnParams {
@@ -40,33 +51,35 @@ struct KnnParams {
     int points;            // N, multiple of 128
     int m_tiles;           // N / 128
     int num_units;         // clouds * m_tiles
+    const float *x_hi, *x_lo;   // tf32 split of the features, leading dimension ld (the A rows are read directly)
+    int64_t ld;
     const float *nxx;      // (rows) -|x_j|^2
-    uint16_t *cand;        // (rows, KNN_CAND_CAP)
-    int32_t *cnt;          // (rows) number of candidates found (may exceed the capacity: overflow)
+    uint32_t *masks;       // (rows, 2, N/32): bit j of [row][0] <=> key > T0, of [row][1] <=> key == T0
+    int dbg;               // IQ_KNN_DBG (scripts/knn_probe.py): 1 = epilogue skips its math, 2 = no MMAs, 4 = no TMA loads
 };
 
 template <int BN, int STAGES, int KMAX>
 struct KnnSmem {
-    static constexpr int A_TILE = TBM * TBK * 4;                   // one 32-wide k-block of the A tile, hi or lo
-    static constexpr int A_BYTES = 2 * (KMAX / TBK) * A_TILE;
     static constexpr int B_TILE = BN * TBK * 4;
     static constexpr int STAGE_BYTES = 2 * B_TILE;
     static constexpr int NB_BYTES = 2048 * 4;
+    static constexpr int XCH_BYTES = 2 * TBM * XCH_STRIDE * 4;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = A_BYTES + STAGES * STAGE_BYTES + NB_BYTES + BAR_BYTES + 1024;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + NB_BYTES + XCH_BYTES + BAR_BYTES + 1024;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// descending bitonic network over 64 registers (672 compare-exchanges, fully unrolled)
-__device__ __forceinline__ void sort64_desc(float (&a)[64])
+// descending bitonic network over W registers (fully unrolled)
+template <int W>
+__device__ __forceinline__ void sort_desc(float (&a)[W])
 {
 #pragma unroll
-    for (int kk = 2; kk <= 64; kk <<= 1) {
+    for (int kk = 2; kk <= W; kk <<= 1) {
 #pragma unroll
         for (int jj = kk >> 1; jj > 0; jj >>= 1) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
+            for (int i = 0; i < W; ++i) {
                 const int l = i ^ jj;
                 if (l > i) {
                     const bool desc = (i & kk) == 0;
@@ -79,37 +92,42 @@ __device__ __forceinline__ void sort64_desc(float (&a)[64])
     }
 }
 
-template <int BN, int STAGES, int KMAX, int NOM>
+template <int BN, int STAGES, int KMAX>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
-gram_knn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
-                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                 const KnnParams p)
 {
     using S = KnnSmem<BN, STAGES, KMAX>;
-    static_assert(BN % 64 == 0 && BN <= 128, "column tile must be 64 or 128");
+    static_assert(BN == 64 || BN == 128, "column tile must be 64 or 128");
+    constexpr int HC = BN / 2;                                       // columns of a tile handled by one epilogue warp
+    constexpr int HG = HC / 32;                                      // 32-column TMEM loads per warp and tile
+    static_assert(HC >= KNN_NOM, "each half must track at least NOM blocks");
+    static_assert(KMAX == 64 || KMAX == 128, "feature width is 64 or 128");
+    constexpr int NACC = (512 - 2 * KMAX) / BN;                      // accumulator buffers: TMEM columns [0, NACC*BN)
+    constexpr uint32_t A_COL = NACC * BN;                            // A hi at [A_COL, A_COL+KMAX), lo right after
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *a_smem = smem;
-    uint8_t *b_smem = smem + S::A_BYTES;
+    uint8_t *b_smem = smem;
     float *nb = reinterpret_cast<float *>(b_smem + STAGES * S::STAGE_BYTES);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(nb) + S::NB_BYTES);
+    float *xch = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(nb) + S::NB_BYTES);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(xch) + S::XCH_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *a_full = empty_bar + STAGES;
     uint64_t *a_empty = a_full + 1;
     uint64_t *tmem_full = a_empty + 1;
-    uint64_t *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *tmem_empty = tmem_full + NACC;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.K + TBK - 1) / TBK;
     const int T = p.points / BN;                                     // column tiles per sweep
-    constexpr uint32_t TMEM_COLS = 2 * BN <= 128 ? 128 : 256;
+    constexpr uint32_t TMEM_COLS = 512;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_ahi); prefetch_tmap(&map_alo); prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
+        prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        mbar_init(a_full, 8); mbar_init(a_empty, 1);
+        for (int a = 0; a < NACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -122,159 +140,220 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_consta
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, a_phase = 0;
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-                const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
-                const int cloud_row0 = cloud * p.points;
-                mbar_wait(a_empty, a_phase ^ 1);                     // MMAs of the previous unit have retired
-                mbar_arrive_expect_tx(a_full, (uint32_t)(2 * kblocks * S::A_TILE));
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            const int cloud_row0 = (unit / p.m_tiles) * p.points;
+            for (int t = 0; t < 2 * T; ++t) {
+                const int b_row0 = cloud_row0 + (t >= T ? t - T : t) * BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    tma_load_2d(a_smem + (2 * kb) * S::A_TILE, &map_ahi, a_full, kb * TBK, cloud_row0 + mt * TBM);
-                    tma_load_2d(a_smem + (2 * kb + 1) * S::A_TILE, &map_alo, a_full, kb * TBK, cloud_row0 + mt * TBM);
-                }
-                a_phase ^= 1;
-                for (int t = 0; t < 2 * T; ++t) {
-                    const int b_row0 = cloud_row0 + (t >= T ? t - T : t) * BN;
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t *st = b_smem + stage * S::STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                        tma_load_2d(st, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
-                        tma_load_2d(st + S::B_TILE, &map_blo, &full_bar[stage], kb * TBK, b_row0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = b_smem + stage * S::STAGE_BYTES;
+                    if (elect_one_sync()) {
+                        if (p.dbg & 4) {                               // probe: no loads, the MMAs chew on stale smem
+                            mbar_arrive(&full_bar[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                            tma_load_2d(st, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
+                            tma_load_2d(st + S::B_TILE, &map_blo, &full_bar[stage], kb * TBK, b_row0);
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-            const uint32_t abase = smem_u32(a_smem);
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-                mbar_wait(a_full, a_phase);
-                a_phase ^= 1;
+        // the whole warp walks the schedule (uniform control flow); one elected lane issues the MMAs and commits
+        constexpr uint32_t idesc = make_idesc(BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+        long long c_a = 0, c_acc = 0, c_full = 0, c_issue = 0, c0 = 0, c1 = 0;   // IQ_KNN_DBG & 16: where the issuer waits
+        const bool prof = (p.dbg & 16) != 0;
+        const long long c_begin = clock64();
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            if (prof) c0 = clock64();
+            mbar_wait(a_full, a_phase);
+            if (prof) c_a += clock64() - c0;
+            a_phase ^= 1;
+            tc_fence_after();
+            for (int t = 0; t < 2 * T; ++t) {
+                if (prof) c0 = clock64();
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if (prof) c_acc += clock64() - c0;
                 tc_fence_after();
-                for (int t = 0; t < 2 * T; ++t) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (prof) c0 = clock64();
+                    mbar_wait(&full_bar[stage], phase);
+                    if (prof) { c1 = clock64(); c_full += c1 - c0; }
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sbase = smem_u32(b_smem + stage * S::STAGE_BYTES);
-                        const uint64_t ahi = make_smem_desc(abase + (2 * kb) * S::A_TILE);
-                        const uint64_t alo = make_smem_desc(abase + (2 * kb + 1) * S::A_TILE);
-                        const uint64_t bhi = make_smem_desc(sbase), blo = make_smem_desc(sbase + S::B_TILE);
+                    const uint32_t sbase = smem_u32(b_smem + stage * S::STAGE_BYTES);
+                    const uint32_t ahi = tmem_base + A_COL + (uint32_t)(kb * TBK), alo = ahi + KMAX;
+                    const uint64_t bhi = make_smem_desc(sbase), blo = make_smem_desc(sbase + S::B_TILE);
+                    if (elect_one_sync()) {
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int term = 0; term < 3; ++term) {        // small terms first
-                            const uint64_t ad = term == 0 ? alo : ahi;
-                            const uint64_t bd = term == 1 ? blo : bhi;
+                            for (int term = 0; term < 3; ++term) {    // small terms first
+                                const uint32_t ad = term == 0 ? alo : ahi;
+                                const uint64_t bd = term == 1 ? blo : bhi;
 #pragma unroll
-                            for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
-                                const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                                umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
+                                for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
+                                    const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                                    umma_tf32_ts(d_tmem, ad + (uint32_t)(ks * UMMA_K), bd + koff, idesc,
+                                                 (kb | term | ks) != 0 ? 1u : 0u);
+                                }
                             }
                         }
                         umma_commit(&empty_bar[stage]);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (kb == kblocks - 1) umma_commit(&tmem_full[acc]);
                     }
-                    umma_commit(&tmem_full[acc]);
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    __syncwarp();
+                    if (prof) c_issue += clock64() - c1;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(a_empty);                                // the resident A tile may be overwritten
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(a_empty);              // the A tile in TMEM may be overwritten
+            __syncwarp();
         }
+        if (prof && blockIdx.x == 0 && lane == 0)
+            printf("gram_knn issuer (block 0): total %lld clk, wait A %lld, wait accumulator %lld, wait B stage %lld, issue %lld\n",
+                   clock64() - c_begin, c_a, c_acc, c_full, c_issue);
     } else {
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                            // which half of every tile's columns
         const int row_in_tile = quad * 32 + lane;
-        const int etid = threadIdx.x - 64;                           // 0..127 among the epilogue threads
+        const int etid = threadIdx.x - 64;                           // 0..255 among the epilogue threads
+        const uint32_t nb_s = smem_u32(nb);
+        const int words = p.points >> 5;
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, a_phase = 0;
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
             const int64_t cloud_row0 = (int64_t)cloud * p.points;
             const int64_t row = cloud_row0 + mt * TBM + row_in_tile;
-            epi_bar_sync();                                          // everyone is done with the previous cloud's norms
-            for (int i = etid; i < p.points; i += 128) nb[i] = __ldg(p.nxx + cloud_row0 + i);
+            // ---- park this unit's A rows in TMEM: half 0 writes the hi part of its row, half 1 the lo part
+            {
+                const float4 *src = reinterpret_cast<const float4 *>((half ? p.x_lo : p.x_hi) + row * p.ld);
+                const uint32_t a_t = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL + (uint32_t)(half * KMAX);
+                mbar_wait(a_empty, a_phase ^ 1);                     // MMAs of the previous unit have retired
+                a_phase ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < KMAX / 32; ++c) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 f = __ldg(src + c * 8 + q);
+                        r[4 * q] = __float_as_uint(f.x); r[4 * q + 1] = __float_as_uint(f.y);
+                        r[4 * q + 2] = __float_as_uint(f.z); r[4 * q + 3] = __float_as_uint(f.w);
+                    }
+                    tmem_st32(a_t + 32 * c, r);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full);
+            }
+            epi_bar_sync();                                          // everyone is done with the previous unit's smem
+            for (int i = etid; i < p.points; i += KNN_EPI_THREADS) nb[i] = __ldg(p.nxx + cloud_row0 + i);
             epi_bar_sync();
 
-            // ---- sweep 1: running maxima of the 64 strided column blocks
-            float bm[64];
+            // ---- sweep 1: running maxima of this half's strided column blocks (column j -> block j mod HC)
+            float bm[HC];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) bm[i] = -INFINITY;
+            for (int i = 0; i < HC; ++i) bm[i] = -INFINITY;
             for (int t = 0; t < T; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HC);
+                const uint32_t nba = nb_s + (uint32_t)(t * BN + half * HC) * 4u;
+                uint32_t v[HG][32];
+                if (!(p.dbg & 1)) {
 #pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 64) {
-                    float v[32];
-                    const float4 *nb4 = reinterpret_cast<const float4 *>(nb + t * BN + c0);
-                    tmem_ld32(taddr + c0, v);
+                for (int g = 0; g < HG; ++g) tmem_ld32_issue(taddr + 32 * g, v[g]);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = nb4[q];
-                        bm[4 * q] = fmaxf(bm[4 * q], fmaf(2.0f, v[4 * q], b.x));
-                        bm[4 * q + 1] = fmaxf(bm[4 * q + 1], fmaf(2.0f, v[4 * q + 1], b.y));
-                        bm[4 * q + 2] = fmaxf(bm[4 * q + 2], fmaf(2.0f, v[4 * q + 2], b.z));
-                        bm[4 * q + 3] = fmaxf(bm[4 * q + 3], fmaf(2.0f, v[4 * q + 3], b.w));
-                    }
-                    tmem_ld32(taddr + c0 + 32, v);
+                for (int g = 0; g < HG; ++g) {
+                    tmem_ld_wait_regs(v[g]);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 b = nb4[8 + q];
-                        bm[32 + 4 * q] = fmaxf(bm[32 + 4 * q], fmaf(2.0f, v[4 * q], b.x));
-                        bm[32 + 4 * q + 1] = fmaxf(bm[32 + 4 * q + 1], fmaf(2.0f, v[4 * q + 1], b.y));
-                        bm[32 + 4 * q + 2] = fmaxf(bm[32 + 4 * q + 2], fmaf(2.0f, v[4 * q + 2], b.z));
-                        bm[32 + 4 * q + 3] = fmaxf(bm[32 + 4 * q + 3], fmaf(2.0f, v[4 * q + 3], b.w));
+                        const float4 b = lds128(nba + 128u * g + 16u * q);
+                        const int o = 32 * g + 4 * q;
+                        bm[o] = fmaxf(bm[o], fmaf(2.0f, __uint_as_float(v[g][4 * q]), b.x));
+                        bm[o + 1] = fmaxf(bm[o + 1], fmaf(2.0f, __uint_as_float(v[g][4 * q + 1]), b.y));
+                        bm[o + 2] = fmaxf(bm[o + 2], fmaf(2.0f, __uint_as_float(v[g][4 * q + 2]), b.z));
+                        bm[o + 3] = fmaxf(bm[o + 3], fmaf(2.0f, __uint_as_float(v[g][4 * q + 3]), b.w));
                     }
+                }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
-            sort64_desc(bm);
-            const float T0 = bm[NOM - 1];                            // >= NOM columns of this row have key >= T0
+            // T0 = NOM-th largest block maximum over both halves: the NOM largest of the union of two descending
+            // lists a, b are { max(a[i], b[NOM-1-i]) }, and T0 is the smallest of them
+            sort_desc<HC>(bm);
+            {
+                float *mine = xch + (half * TBM + row_in_tile) * XCH_STRIDE;
+#pragma unroll
+                for (int i = 0; i < KNN_NOM; ++i) mine[i] = bm[i];
+            }
+            epi_bar_sync();
+            float T0 = INFINITY;
+            {
+                const float *other = xch + ((half ^ 1) * TBM + row_in_tile) * XCH_STRIDE;
+#pragma unroll
+                for (int i = 0; i < KNN_NOM; ++i) T0 = fminf(T0, fmaxf(bm[i], other[KNN_NOM - 1 - i]));
+            }
 
-            // ---- sweep 2: collect the columns at or above the threshold
-            int n = 0, neq = 0;
-            uint16_t *list = p.cand + row * KNN_CAND_CAP;
+            // ---- sweep 2: one bit per column for key > T0 and key == T0
+            uint32_t *mrow = p.masks + row * (int64_t)(2 * words);
             for (int t = 0; t < T; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    float v[32];
-                    const float4 *nb4 = reinterpret_cast<const float4 *>(nb + t * BN + c0);
-                    tmem_ld32(taddr + c0, v);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HC);
+                const uint32_t nba = nb_s + (uint32_t)(t * BN + half * HC) * 4u;
+                uint32_t v[HG][32];
+                uint32_t gtw[HG] = {}, eqw[HG] = {};
+                if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int g = 0; g < HG; ++g) tmem_ld32_issue(taddr + 32 * g, v[g]);
+#pragma unroll
+                for (int g = 0; g < HG; ++g) {
+                    tmem_ld_wait_regs(v[g]);
+                    uint32_t mgt[4] = {0u, 0u, 0u, 0u}, meq[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 b = nb4[q];
-                        const float kq[4] = {fmaf(2.0f, v[4 * q], b.x), fmaf(2.0f, v[4 * q + 1], b.y),
-                                             fmaf(2.0f, v[4 * q + 2], b.z), fmaf(2.0f, v[4 * q + 3], b.w)};
+                        const float4 b = lds128(nba + 128u * g + 16u * q);
+                        const float kq[4] = {fmaf(2.0f, __uint_as_float(v[g][4 * q]), b.x),
+                                             fmaf(2.0f, __uint_as_float(v[g][4 * q + 1]), b.y),
+                                             fmaf(2.0f, __uint_as_float(v[g][4 * q + 2]), b.z),
+                                             fmaf(2.0f, __uint_as_float(v[g][4 * q + 3]), b.w)};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const bool eq = kq[e] == T0;
-                            if (kq[e] > T0 || (eq && neq < NOM)) {
-                                if (n < KNN_CAND_CAP) list[n] = (uint16_t)(t * BN + c0 + 4 * q + e);
-                                ++n;
-                            }
-                            neq += eq ? 1 : 0;
+                            if (kq[e] > T0) mgt[e] |= 1u << (4 * q + e);
+                            if (kq[e] == T0) meq[e] |= 1u << (4 * q + e);
                         }
                     }
+                    gtw[g] = mgt[0] | mgt[1] | mgt[2] | mgt[3];
+                    eqw[g] = meq[0] | meq[1] | meq[2] | meq[3];
+                }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                const int w0 = (t * BN + half * HC) >> 5;
+                if (HG == 2) {
+                    *reinterpret_cast<uint2 *>(mrow + w0) = make_uint2(gtw[0], gtw[HG - 1]);
+                    *reinterpret_cast<uint2 *>(mrow + words + w0) = make_uint2(eqw[0], eqw[HG - 1]);
+                } else {
+                    mrow[w0] = gtw[0];
+                    mrow[words + w0] = eqw[0];
+                }
             }
-            p.cnt[row] = n;
         }
     }
 
@@ -286,24 +365,72 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_consta
     }
 }
 
+__device__ __forceinline__ int warp_exclusive_scan(int x, int lane, int &total)
+{
+    int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    total = __shfl_sync(FULL, incl, 31);
+    return incl - x;
+}
+
 // ---- exact decision among the candidates ------------------------------------------------------------------
-// One warp per row.  Half-warp h handles candidate slots c with (c & 16) == 16 h, so the 16 lanes of a half read one
-// feature row as consecutive float4 (coalesced) and the lane that keeps the result, c & 31, lies in the same half.
+// One warp per row.  The masks are decoded into the warp's candidate list (index order); half-warp h then handles the
+// candidate slots c with (c & 16) == 16 h, so the 16 lanes of a half read one feature row as consecutive float4
+// (coalesced) and the lane that keeps the result, c & 31, lies in the same half.
 template <int CV>                                                    // CV = C / 64: float4 per lane and row
 __global__ void __launch_bounds__(256)
-knn_rerank_list_kernel(const float *__restrict__ x, int64_t ld, const uint16_t *__restrict__ cand,
-                       const int32_t *__restrict__ cnt, int64_t rows, int N, int k, int32_t *__restrict__ idx)
+knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *__restrict__ masks, int64_t rows, int N,
+                       int k, int32_t *__restrict__ idx, int32_t *__restrict__ cnt)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint16_t cand_s[8][KNN_CAND_CAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
-    const int n = cnt[row];
+    const int words = N >> 5;
+    const uint32_t *mg = masks + row * (int64_t)(2 * words), *me = mg + words;
+    uint16_t *cl = cand_s[wib];
+    int n = 0;
+    for (int w0 = 0; w0 < words; w0 += 32) {                          // every column above the threshold
+        const int w = w0 + lane;
+        uint32_t m = w < words ? __ldg(mg + w) : 0u;
+        int tot;
+        int pos = n + warp_exclusive_scan(__popc(m), lane, tot);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < KNN_CAND_CAP) cl[pos] = (uint16_t)(w * 32 + b);
+            ++pos;
+        }
+        n += tot;
+    }
+    int need = KNN_NOM - n;                                            // then the lowest-index ties, up to NOM in all
+    for (int w0 = 0; w0 < words && need > 0; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t m = w < words ? __ldg(me + w) : 0u;
+        int tot;
+        int e = warp_exclusive_scan(__popc(m), lane, tot);
+        while (m && e < need) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            cl[n + e] = (uint16_t)(w * 32 + b);                       // n + e < NOM <= capacity
+            ++e;
+        }
+        const int took = min(tot, need);
+        n += took;
+        need -= took;
+    }
+    if (lane == 0) cnt[row] = n;
     if (n > KNN_CAND_CAP || n < k) return;                           // redone by knn_exact_rows_kernel
+    __syncwarp();
     const int64_t cloud0 = (row / N) * N;
     const int sub = lane & 15, half = lane >> 4;
     int myj[2];
-    myj[0] = lane < n ? (int)cand[row * KNN_CAND_CAP + lane] : 0;
-    myj[1] = lane + 32 < n ? (int)cand[row * KNN_CAND_CAP + 32 + lane] : 0;
+    myj[0] = lane < n ? (int)cl[lane] : 0;
+    myj[1] = lane + 32 < n ? (int)cl[32 + lane] : 0;
     float4 xi[CV];
 #pragma unroll
     for (int q = 0; q < CV; ++q) xi[q] = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + q * 16 + sub);
@@ -312,11 +439,11 @@ knn_rerank_list_kernel(const float *__restrict__ x, int64_t ld, const uint16_t *
     for (int r = 0; r < rounds; ++r) {
 #pragma unroll 4
         for (int tt = 0; tt < 16; ++tt) {
-            const int slot = tt + 16 * half;                         // candidate slot (within this round) of my half
-            const int j = __shfl_sync(FULL, myj[r], slot);
-            const bool valid = r * 32 + slot < n;
+            const int slot = r * 32 + tt + 16 * half;                // candidate slot of my half
+            const bool valid = slot < n;
             double acc = 0.0;
             if (valid) {
+                const int j = cl[slot];
                 const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
 #pragma unroll
                 for (int q = 0; q < CV; ++q) {
@@ -328,7 +455,7 @@ knn_rerank_list_kernel(const float *__restrict__ x, int64_t ld, const uint16_t *
             }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (valid && lane == slot) myd[r] = acc;
+            if (valid && lane == (slot & 31)) myd[r] = acc;
         }
     }
     // rank of every candidate under (distance, index); the reduction order above is fixed, so equal points give
@@ -336,7 +463,7 @@ knn_rerank_list_kernel(const float *__restrict__ x, int64_t ld, const uint16_t *
     int rank0 = 0, rank1 = 0;
     for (int s = 0; s < n; ++s) {
         const double o = s < 32 ? __shfl_sync(FULL, myd[0], s) : __shfl_sync(FULL, myd[1], s - 32);
-        const int oj = s < 32 ? __shfl_sync(FULL, myj[0], s) : __shfl_sync(FULL, myj[1], s - 32);
+        const int oj = cl[s];
         rank0 += (o < myd[0] || (o == myd[0] && oj < myj[0])) ? 1 : 0;
         rank1 += (o < myd[1] || (o == myd[1] && oj < myj[1])) ? 1 : 0;
     }
@@ -344,8 +471,8 @@ knn_rerank_list_kernel(const float *__restrict__ x, int64_t ld, const uint16_t *
     if (lane + 32 < n && rank1 < k) idx[row * k + rank1] = myj[1];
 }
 
-// ---- exhaustive redo of a row (overflowed or short candidate list): distances to every point of the cloud, the 32
-// nearest by the float32-rounded distance, then the same float64 (distance, index) ranking.  Slow and rarely taken.
+// ---- exhaustive redo of a row (overflowed or short candidate set): k rounds of "nearest point after the previous
+// pick" under (float64 distance, index).  O(k N C) per row, slow and normally never taken.
 __global__ void __launch_bounds__(256)
 knn_exact_rows_kernel(const float *__restrict__ x, int64_t ld, int C, const int32_t *__restrict__ cnt, int64_t rows,
                       int N, int k, int32_t *__restrict__ idx)
@@ -362,13 +489,11 @@ knn_exact_rows_kernel(const float *__restrict__ x, int64_t ld, int C, const int3
         double acc = 0.0;
         for (int c = 0; c < (C >> 2); ++c) {
             const float4 a = __ldg(xi + c), b = __ldg(xj + c);
-            // same grouping as knn_rerank_list_kernel is not needed here: this kernel decides the whole row itself
             const double d0 = (double)(a.x - b.x), d1 = (double)(a.y - b.y), d2 = (double)(a.z - b.z), d3 = (double)(a.w - b.w);
             acc = fma(d0, d0, acc); acc = fma(d1, d1, acc); acc = fma(d2, d2, acc); acc = fma(d3, d3, acc);
         }
         return acc;
     };
-    // k rounds of "smallest (distance, index) larger than the previous pick": O(k N C) per row, no scratch
     double last_d = -1.0;
     int last_j = -1;
     for (int r = 0; r < k; ++r) {
@@ -391,24 +516,23 @@ knn_exact_rows_kernel(const float *__restrict__ x, int64_t ld, int C, const int3
     }
 }
 
-template <int BN, int STAGES, int KMAX, int NOM>
+template <int BN, int STAGES, int KMAX>
 int launch_variant(const float *x_hi, const float *x_lo, int64_t ld, int64_t rows, const KnnParams &p, cudaStream_t st)
 {
     using S = KnnSmem<BN, STAGES, KMAX>;
     static_assert(S::TOTAL <= 232448, "shared memory budget exceeded");
-    CUtensorMap mahi, malo, mbhi, mblo;
-    if (int rc = make_map(&mahi, x_hi, rows, p.K, ld, TBM)) return rc;
-    if (int rc = make_map(&malo, x_lo, rows, p.K, ld, TBM)) return rc;
+    IQ_CHECK(p.K == KMAX, "knn_features_tc: feature width does not match the kernel variant");
+    CUtensorMap mbhi, mblo;
     if (int rc = make_map(&mbhi, x_hi, rows, p.K, ld, BN)) return rc;
     if (int rc = make_map(&mblo, x_lo, rows, p.K, ld, BN)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        IQ_CUDA(cudaFuncSetAttribute(gram_knn_kernel<BN, STAGES, KMAX, NOM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IQ_CUDA(cudaFuncSetAttribute(gram_knn_kernel<BN, STAGES, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      S::TOTAL));
         attr_set = true;
     }
     const int grid = std::min(p.num_units, sm_count());
-    gram_knn_kernel<BN, STAGES, KMAX, NOM><<<grid, KNN_THREADS, S::TOTAL, st>>>(mahi, malo, mbhi, mblo, p);
+    gram_knn_kernel<BN, STAGES, KMAX><<<grid, KNN_THREADS, S::TOTAL, st>>>(mbhi, mblo, p);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -422,7 +546,7 @@ bool knn_features_tc_supported(int64_t N, int C, int k)
 }
 
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
-                           int64_t clouds, int64_t N, int k, uint16_t *cand, int32_t *cnt, int32_t *idx,
+                           int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
                            cudaStream_t st)
 {
     IQ_CHECK(knn_features_tc_supported(N, C, k), "knn_features_tc: unsupported shape");
@@ -432,18 +556,20 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
     IQ_CHECK(rows < (int64_t)1 << 31, "knn_features_tc: too many rows");
     KnnParams p;
     p.K = C; p.points = (int)N; p.m_tiles = (int)(N / TBM); p.num_units = (int)(clouds * p.m_tiles);
-    p.nxx = nxx; p.cand = cand; p.cnt = cnt;
+    p.nxx = nxx; p.masks = masks; p.x_hi = x_hi; p.x_lo = x_lo; p.ld = ld;
+    const char *dbg = getenv("IQ_KNN_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
     {
-        ProfileScope _ps("tc_gram_knn", st);
-        int rc = C <= 64 ? launch_variant<128, 4, 64, 24>(x_hi, x_lo, ld, rows, p, st)
-                         : launch_variant<64, 5, 128, 24>(x_hi, x_lo, ld, rows, p, st);
+        ProfileScope _ps(C <= 64 ? "tc_gram_knn_c64" : "tc_gram_knn_c128", st);
+        int rc = C == 64 ? launch_variant<128, 6, 64>(x_hi, x_lo, ld, rows, p, st)
+                         : launch_variant<128, 6, 128>(x_hi, x_lo, ld, rows, p, st);
         if (rc) return rc;
     }
     {
         ProfileScope _ps("knn_rerank", st);
         const unsigned grid = (unsigned)ceil_div(rows * 32, 256);
-        if (C == 64) knn_rerank_list_kernel<1><<<grid, 256, 0, st>>>(x, ld, cand, cnt, rows, (int)N, k, idx);
-        else knn_rerank_list_kernel<2><<<grid, 256, 0, st>>>(x, ld, cand, cnt, rows, (int)N, k, idx);
+        if (C == 64) knn_rerank_mask_kernel<1><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        else knn_rerank_mask_kernel<2><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
         IQ_COUNT_LAUNCH();
         IQ_LAUNCH_CHECK();
         knn_exact_rows_kernel<<<grid, 256, 0, st>>>(x, ld, C, cnt, rows, (int)N, k, idx);

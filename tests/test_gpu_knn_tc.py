@@ -102,7 +102,7 @@ def test_dgcnn_forward_uses_the_fused_knn_and_matches_fp32_engine():
     tc = model.forward_point_major(x).cpu().numpy()
     rep = _lib.profile_report()
     _lib.profile_enable(False)
-    assert "tc_gram_knn" in rep and rep["tc_gram_knn"][1] == 3
+    assert rep["tc_gram_knn_c64"][1] == 2 and rep["tc_gram_knn_c128"][1] == 1
     model.set_engine("fp32")
     fp = model.forward_point_major(x).cpu().numpy()
     assert np.abs(tc - fp).max() / np.abs(fp).max() <= 1e-3
