@@ -378,14 +378,18 @@ __device__ __forceinline__ int warp_exclusive_scan(int x, int lane, int &total)
 }
 
 // ---- exact decision among the candidates ------------------------------------------------------------------
-// One warp per row.  The masks are decoded into the warp's candidate list (index order); half-warp h then handles the
-// candidate slots c with (c & 16) == 16 h, so the 16 lanes of a half read one feature row as consecutive float4
-// (coalesced) and the lane that keeps the result, c & 31, lies in the same half.
-template <int CV>                                                    // CV = C / 64: float4 per lane and row
-__global__ void __launch_bounds__(256)
+// One warp per row.  The masks are decoded into the warp's candidate list (index order).  LPC = C/16 lanes share a
+// candidate (each lane 16 channels as 4 float4, interleaved so a group reads 64 contiguous bytes per instruction), so
+// a warp evaluates 32/LPC candidates at a time; the usual case of <= 32 candidates is then ordered by a 15-step
+// bitonic network over the lanes, keyed by (float64 distance, index).
+template <int C>
+__global__ void __launch_bounds__(256, 3)
 knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *__restrict__ masks, int64_t rows, int N,
                        int k, int32_t *__restrict__ idx, int32_t *__restrict__ cnt)
 {
+    constexpr int LPC = C / 16;                                      // lanes per candidate: 4 (C = 64) or 8 (C = 128)
+    constexpr int CPI = 32 / LPC;                                    // candidates per iteration
+    constexpr int ITERS = 32 / CPI;                                  // iterations per batch of 32 candidates
     __shared__ uint16_t cand_s[8][KNN_CAND_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -427,39 +431,62 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
     if (n > KNN_CAND_CAP || n < k) return;                           // redone by knn_exact_rows_kernel
     __syncwarp();
     const int64_t cloud0 = (row / N) * N;
-    const int sub = lane & 15, half = lane >> 4;
-    int myj[2];
-    myj[0] = lane < n ? (int)cl[lane] : 0;
-    myj[1] = lane + 32 < n ? (int)cl[32 + lane] : 0;
-    float4 xi[CV];
+    const int grp = lane / LPC, sub = lane % LPC;
+    float4 xi[4];
 #pragma unroll
-    for (int q = 0; q < CV; ++q) xi[q] = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + q * 16 + sub);
+    for (int q = 0; q < 4; ++q) xi[q] = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + q * LPC + sub);
+    const int batches = n > 32 ? 2 : 1;
     double myd[2] = {INFINITY, INFINITY};
-    const int rounds = n > 32 ? 2 : 1;
-    for (int r = 0; r < rounds; ++r) {
-#pragma unroll 4
-        for (int tt = 0; tt < 16; ++tt) {
-            const int slot = r * 32 + tt + 16 * half;                // candidate slot of my half
-            const bool valid = slot < n;
-            double acc = 0.0;
-            if (valid) {
-                const int j = cl[slot];
-                const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
+    int myj[2] = {0x7fffffff, 0x7fffffff};
 #pragma unroll
-                for (int q = 0; q < CV; ++q) {
-                    const float4 b = __ldg(xj + q * 16 + sub);
+    for (int bt = 0; bt < 2; ++bt) {
+        if (bt >= batches) break;
+        double dacc[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int slot = bt * 32 + it * CPI + grp;
+            double acc = 0.0;
+            if (slot < n) {
+                const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + cl[slot]) * ld);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = __ldg(xj + q * LPC + sub);
                     const double d0 = (double)(xi[q].x - b.x), d1 = (double)(xi[q].y - b.y);
                     const double d2 = (double)(xi[q].z - b.z), d3 = (double)(xi[q].w - b.w);
                     acc = fma(d0, d0, acc); acc = fma(d1, d1, acc); acc = fma(d2, d2, acc); acc = fma(d3, d3, acc);
                 }
             }
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (valid && lane == (slot & 31)) myd[r] = acc;
+            for (int o = LPC / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            dacc[it] = acc;
         }
+        // candidate slot bt*32 + L moves to lane L: it was evaluated in iteration L / CPI by group L % CPI
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const double v = __shfl_sync(FULL, dacc[it], (lane % CPI) * LPC);
+            if (lane / CPI == it) myd[bt] = v;
+        }
+        if (bt * 32 + lane < n) myj[bt] = cl[bt * 32 + lane];
+        else myd[bt] = INFINITY;
     }
-    // rank of every candidate under (distance, index); the reduction order above is fixed, so equal points give
-    // bit-equal distances and fall back to the index
+    // the reduction order above is fixed, so coincident points give bit-equal distances and fall back to the index
+    if (batches == 1) {
+        double d = myd[0];
+        int j = myj[0];
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                const double od = __shfl_xor_sync(FULL, d, jj);
+                const int oj = __shfl_xor_sync(FULL, j, jj);
+                const bool other_first = od < d || (od == d && oj < j);
+                const bool want_first = ((lane & kk) == 0) == ((lane & jj) == 0);   // this lane keeps the smaller key
+                if (other_first == want_first) { d = od; j = oj; }
+            }
+        }
+        if (lane < k) idx[row * k + lane] = j;
+        return;
+    }
     int rank0 = 0, rank1 = 0;
     for (int s = 0; s < n; ++s) {
         const double o = s < 32 ? __shfl_sync(FULL, myd[0], s) : __shfl_sync(FULL, myd[1], s - 32);
@@ -568,8 +595,8 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
     {
         ProfileScope _ps("knn_rerank", st);
         const unsigned grid = (unsigned)ceil_div(rows * 32, 256);
-        if (C == 64) knn_rerank_mask_kernel<1><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
-        else knn_rerank_mask_kernel<2><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        if (C == 64) knn_rerank_mask_kernel<64><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        else knn_rerank_mask_kernel<128><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
         IQ_COUNT_LAUNCH();
         IQ_LAUNCH_CHECK();
         knn_exact_rows_kernel<<<grid, 256, 0, st>>>(x, ld, C, cnt, rows, (int)N, k, idx);
