@@ -169,37 +169,52 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+# tcgen05 kind::tf32 issue rate measured on this pool's B200 by scripts/microbench/umma_rate.cu (64 clk per 128x128x8
+# MMA, SS and TS mode): the ceiling of the EXECUTED tf32 FLOPs of the 3xTF32 kernels
+TF32_TFLOPS_MEASURED = 1100.0
+
+
 def kernel_work(a):
-    """Algorithmic work per forward (one masked cloud) of the kernel families, for the roofline leg.
-    "tensor": FLOPs = 2*MAC of the product the kernel evaluates (logical fp32 product; the tcgen05 kernels
-    execute 3 TF32 MMAs per logical MAC).  "hbm": compulsory bytes."""
+    """Algorithmic work per forward (one masked cloud) of the kernel families, for the roofline leg (DESIGN.md
+    section 4).  "tensor": (logical FLOPs = 2*MAC of the fp32 product the kernel evaluates, tcgen05 MMAs executed per
+    logical MAC: 3 for 3xTF32, 6 for the two-sweep Gram).  "hbm": compulsory bytes (every operand read once, every
+    result written once; gathers that hit L2 are not counted)."""
     N, k = a.points, 20
     mac = lambda *terms: 2.0 * sum(r * ci * co for r, ci, co in terms)
-    w = {"mask_shapley": ("hbm", 12.0 * N), "reward": ("hbm", 44.0), "shapley_accumulate": ("hbm", 4.0 + 8.0 * R / (R + 1))}
+    T = lambda flops, mult=3: ("tensor", flops, mult)
+    H = lambda nbytes: ("hbm", nbytes, 1)
+    w = {"mask_shapley": H(12.0 * N), "reward": H(44.0), "shapley_accumulate": H(4.0 + 8.0 * R / (R + 1))}
     if a.model in ("dgcnn", "gcnn"):
-        w["tc_conv5_pool"] = w["sgemm_conv5_pool"] = ("tensor", mac((N, 512, 1024)))
+        w["tc_conv5_pool"] = T(mac((N, 512, 1024)))
+        w["sgemm_conv5_pool"] = T(mac((N, 512, 1024)), 1)
+        couts = (64, 64, 128, 256)
         if a.model == "dgcnn":
-            w["sgemm_edge_pq"] = ("tensor", mac((N, 3, 128), (N, 64, 128), (N, 64, 256)))
-            w["tc_edge_pq"] = ("tensor", mac((N, 128, 512)))
-            w["sgemm_gram"] = w["tc_gram"] = ("tensor", mac((N, N, 64), (N, N, 64), (N, N, 128)))
-            w["topk_rows"] = ("hbm", 3.0 * (4.0 * N * N + 4.0 * N * k))
+            w["sgemm_edge_pq"] = T(mac((N, 3, 128), (N, 64, 128), (N, 64, 256)), 1)
+            w["tc_edge_pq"] = T(mac((N, 128, 512)))
+            w["sgemm_gram"] = T(mac((N, N, 64), (N, N, 64), (N, N, 128)), 1)
+            w["tc_gram_knn_c64"] = T(mac((N, N, 64)) * 2, 6)                  # two layers with 64-wide features
+            w["tc_gram_knn_c128"] = T(mac((N, N, 128)), 6)
+            w["topk_rows"] = H(3.0 * (4.0 * N * N + 4.0 * N * k))
+            # masks (2 bits per column pair) + the feature rows once + neighbour lists, three layers
+            w["knn_rerank"] = H(3.0 * (N * N / 4.0 + 4.0 * N * k) + 4.0 * N * (64 + 64 + 128))
         else:
-            w["sgemm_edge_pq"] = ("tensor", mac((N, 3, 128)))
-            w["tc_edge_pq"] = ("tensor", mac((N, 64, 128), (N, 64, 256), (N, 128, 512)))
-        w["gather_max"] = ("hbm", sum(4.0 * N * (2 * c + 3 * c) + 4.0 * N * k for c in (64, 64, 128, 256)))
-        w["knn_xyz"] = ("hbm", 12.0 * N + 4.0 * N * k)
+            w["sgemm_edge_pq"] = T(mac((N, 3, 128)), 1)
+            w["tc_edge_pq"] = T(mac((N, 64, 128), (N, 64, 256), (N, 128, 512)))
+        # P|Q rows read once, neighbour lists, fp32 output + its tf32 hi/lo split + the squared norm
+        w["gather_max"] = H(sum(4.0 * N * 2 * c + 4.0 * N * k + 3 * 4.0 * N * c + 4.0 * N for c in couts))
+        w["knn_xyz"] = H(12.0 * N + 4.0 * N * k)
     elif a.model == "pointnet":
-        w["tc_conv_pool"] = ("tensor", mac((N, 128, 1024)) * 3)
-        w["tc_conv"] = ("tensor", mac((N, 64, 128)) * 3 + mac((N, 64, 64)))
+        w["tc_conv_pool"] = T(mac((N, 128, 1024)) * 3)
+        w["tc_conv"] = T(mac((N, 64, 128)) * 3 + mac((N, 64, 64)))
     elif a.model == "pointnet2":
-        w["tc_sa_mlp2"] = ("tensor", mac((8192, 32, 32), (16384, 64, 64), (65536, 64, 96), (4096, 64, 64),
-                                         (8192, 128, 128), (16384, 128, 128)))
-        w["tc_sa_mlp3_pool"] = ("tensor", mac((8192, 32, 64), (16384, 64, 128), (65536, 96, 128), (4096, 64, 128),
-                                              (8192, 128, 256), (16384, 128, 256)))
+        w["tc_sa_mlp2"] = T(mac((8192, 32, 32), (16384, 64, 64), (65536, 64, 96), (4096, 64, 64),
+                                (8192, 128, 128), (16384, 128, 128)))
+        w["tc_sa_mlp3_pool"] = T(mac((8192, 32, 64), (16384, 64, 128), (65536, 96, 128), (4096, 64, 128),
+                                     (8192, 128, 256), (16384, 128, 256)))
     elif a.model == "pointconv":
-        w["tc_sa_mlp2"] = ("tensor", mac((16384, 64, 64), (8192, 128, 128), (128, 256, 512)))
-        w["tc_sa_mlp3"] = ("tensor", mac((16384, 64, 128), (8192, 128, 256), (128, 512, 1024)))
-        w["tc_sa_linear"] = ("tensor", mac((512, 2048, 128), (128, 4096, 256)))
+        w["tc_sa_mlp2"] = T(mac((16384, 64, 64), (8192, 128, 128), (128, 256, 512)))
+        w["tc_sa_mlp3"] = T(mac((16384, 64, 128), (8192, 128, 256), (128, 512, 1024)))
+        w["tc_sa_linear"] = T(mac((512, 2048, 128), (128, 4096, 256)))
     return w
 
 
@@ -329,22 +344,34 @@ def run_b200(a):
         tot = sum(ms for ms, _ in rep.values())
         breakdown = {k: {"ms": round(ms, 3), "launches": n, "share": round(ms / tot, 4)} for k, (ms, n) in
                      sorted(rep.items(), key=lambda kv: -kv[1][0])}
+        kernels = []
         for name, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
             if name not in work:
                 continue
-            bound, per_fwd = work[name]
+            bound, per_fwd, mult = work[name]
             per_launch = per_fwd * fwd_per_step / n
             dur = ms * 1e-3 / n
             if bound == "tensor":
                 ach, peak, unit = per_launch / dur / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
             else:
                 ach, peak, unit = per_launch / dur / 1e9, pk["hbm_gbs"], "GB/s"
-            roofline = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                        "traffic": None, "avg_launch_ms": dur * 1e3, "launches_per_step": n,
-                        "algorithmic_per_launch": per_launch, "peak_source": pk["source"],
-                        "note": "peak = measured dense bf16 (sustained) / copy bandwidth of MEASURED_PEAKS.json; "
-                                "the kernel computes in fp32"}
-            break
+            k = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                 "traffic": None, "avg_launch_ms": dur * 1e3, "launches_per_step": n, "share_of_step": ms / tot,
+                 "algorithmic_per_launch": per_launch, "peak_source": pk["source"]}
+            if bound == "tensor":
+                # the kernels compute fp32 products as `mult` tf32 MMAs each: the executed rate is what the tensor pipe
+                # sees, measured against the tf32 issue rate of this GPU (scripts/microbench/umma_rate.cu)
+                k["mmas_per_logical_mac"] = mult
+                k["executed_tflops"] = ach * mult
+                k["executed_frac_of_tf32_peak"] = ach * mult / TF32_TFLOPS_MEASURED if mult > 1 else None
+            kernels.append(k)
+        if kernels:
+            roofline = dict(kernels[0])
+            roofline["note"] = ("dominant kernel of the step by device time; peak = MEASURED_PEAKS.json (dense bf16 sustained "
+                                "for tensor kernels, copy bandwidth for the others); achieved = algorithmic work / "
+                                "CUDA-event duration; tensor kernels evaluate exact-fp32-grade products as 3 (Gram: 6) tf32 "
+                                "MMAs per MAC, see executed_tflops; every kernel of the step is listed under `kernels`")
+        breakdown = {"by_kernel": breakdown, "kernels": kernels}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -24,6 +24,8 @@
 //                        models/pointnet.py:35,83 of the reference).
 //   Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i
 //   overlaps the main loop of tile i+1.
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 #include "kernels.cuh"
 
@@ -58,6 +60,7 @@ struct TcParams {
     int64_t *out_arg;            // (clouds, Cout)
     int64_t ld_out;
     int cout;
+    int dbg;                     // IQ_TC_DBG (scripts/tc_probe.py): 1 = STORE epilogue skips its math and stores
 };
 
 template <int BN, int STAGES>
@@ -66,21 +69,47 @@ struct TcSmem {
     static constexpr int B_BYTES = BN * TBK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+    static constexpr int OUT_BYTES = 4 * 2 * 4096;                          // per epilogue warp: two 32 x 32 store boxes
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;   // +1024: alignment slack
 };
 
 constexpr int tmem_cols_for(int bn) { return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512; }
+
+// One warp's 32 x 32 block -> 128B-swizzled box in shared memory -> TMA store.  Boxes alternate between two buffers;
+// before reusing one, the issuing lane waits until at most one earlier store is still reading shared memory.
+__device__ __forceinline__ void store_box(const CUtensorMap *map, const float (&val)[32], uint32_t box0, int &nbox, int lane,
+                                          int sw, int col, int row)
+{
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    const uint32_t boxb = box0 + (uint32_t)(nbox & 1) * 4096u;
+    const uint32_t mine = boxb + (uint32_t)lane * 128u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        sts128(mine + (uint32_t)((c ^ sw) << 4), val[4 * c], val[4 * c + 1], val[4 * c + 2], val[4 * c + 3]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map), "r"(boxb), "r"(col), "r"(row)
+                     : "memory");
+        bulk_commit();
+    }
+    ++nbox;
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-               const TcParams p)
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_chi,
+               const __grid_constant__ CUtensorMap map_clo, const TcParams p)
 {
     using S = TcSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * S::STAGE_BYTES);
+    uint8_t *out_stage = smem + STAGES * S::STAGE_BYTES;                    // 1024-byte aligned (stages are multiples of 1 KB)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(out_stage + S::OUT_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full = empty_bar + STAGES;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -177,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     } else {
         const int quad = warp & 3;                                       // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;
-        int acc = 0;
+        int acc = 0, nbox = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             float run_max = -INFINITY, run_sum = 0.0f;
@@ -189,31 +218,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
                 if (p.mode == 0) {
+                    // The accumulator arrives one ROW per thread; stored that way a warp touches 32 rows per instruction
+                    // and the epilogue, not the MMAs, paced the kernel (measured 76 us vs 25 us without it).  Each warp
+                    // now writes its 32 x 32 block into a 128B-swizzled shared-memory box (conflict-free 16-byte
+                    // stores) and one lane hands it to TMA: the stores leave asynchronously, fully coalesced.
                     const int nt = unit % p.n_tiles;
-                    const int64_t coff = (int64_t)(a_row0 + row_in_tile) * p.ldc + (int64_t)nt * BN;
+                    const uint32_t box0 = smem_u32(out_stage) + (uint32_t)(warp - 2) * 8192u;
+                    const int out_row = a_row0 + quad * 32, sw = lane & 7;
 #pragma unroll 1
                     for (int c0 = 0; c0 < BN; c0 += 32) {
+                        if (p.dbg & 1) break;
+                        float bv[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bv[i] = p.bias ? __ldg(p.bias + b_row0 + c0 + i) : 0.0f;
                         float v[32];
                         tmem_ld32(taddr + c0, v);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float b = p.bias ? __ldg(p.bias + b_row0 + c0 + i) : 0.0f;
-                            v[i] = apply_act(fmaf(p.alpha, v[i], b), p.act);
-                        }
-                        if (p.C) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                *reinterpret_cast<float4 *>(p.C + coff + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        }
+                        for (int i = 0; i < 32; ++i) v[i] = apply_act(fmaf(p.alpha, v[i], bv[i]), p.act);
+                        const int col = nt * BN + c0;
+                        if (p.C) store_box(&map_c, v, box0, nbox, lane, sw, col, out_row);
                         if (p.C_hi) {
+                            float h[32];
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float h[4], l[4];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) { h[q] = tf32_round(v[i + q]); l[q] = tf32_round(v[i + q] - h[q]); }
-                                *reinterpret_cast<float4 *>(p.C_hi + coff + c0 + i) = make_float4(h[0], h[1], h[2], h[3]);
-                                *reinterpret_cast<float4 *>(p.C_lo + coff + c0 + i) = make_float4(l[0], l[1], l[2], l[3]);
-                            }
+                            for (int i = 0; i < 32; ++i) { h[i] = tf32_round(v[i]); v[i] = tf32_round(v[i] - h[i]); }
+                            store_box(&map_chi, h, box0, nbox, lane, sw, col, out_row);
+                            store_box(&map_clo, v, box0, nbox, lane, sw, col, out_row);
                         }
                     }
                 } else {
@@ -262,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         }
     }
 
+    if (warp >= 2 && lane == 0) bulk_wait_all();                     // every TMA store of this warp has landed
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -329,13 +359,22 @@ static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_
     if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
     if (int rc = make_map(&mbhi, g.B_hi, b_rows, g.K, g.ldb, BN)) return rc;
     if (int rc = make_map(&mblo, g.B_lo, b_rows, g.K, g.ldb, BN)) return rc;
+    // STORE outputs leave through TMA: 32 x 32 boxes (128 bytes wide) over each fp32 output matrix
+    CUtensorMap mc = mahi, mchi = mahi, mclo = mahi;
+    if (g.mode == 0) {
+        if (g.C) { if (int rc = make_map(&mc, g.C, g.M, g.N, g.ldc, 32)) return rc; }
+        if (g.C_hi) {
+            if (int rc = make_map(&mchi, g.C_hi, g.M, g.N, g.ldc, 32)) return rc;
+            if (int rc = make_map(&mclo, g.C_lo, g.M, g.N, g.ldc, 32)) return rc;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         IQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
     const int grid = std::min(p.num_units, sm_count());
-    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(mahi, malo, mbhi, mblo, p);
+    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(mahi, malo, mbhi, mblo, mc, mchi, mclo, p);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -347,6 +386,8 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
     IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape");
     TcParams p = {};
     p.K = g.K; p.mode = g.mode; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
+    const char *dbg = getenv("IQ_TC_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
     int64_t a_rows, b_rows;
     int bn;
     if (g.mode == 0) {

@@ -376,6 +376,66 @@ gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__r
     }
 }
 
+// ---- EdgeConv aggregation with the neighbour table staged in shared memory ----------------------------------------
+// The gather above reads k * Cout * 4 bytes per point out of L2 (168 MB per 32 clouds at Cout = 64) and is bound by
+// the L2 -> SM path.  Here a CTA owns (cloud, 32-channel slice, range of points): the slice of P for ALL points of the
+// cloud (N x 128 B) is copied once into shared memory with cp.async and the k gathers per point become LDS.128 -- 8
+// lanes per point read one 128-byte row, so every quarter-warp access is conflict free.
+constexpr int GMS_THREADS = 1024;             // one CTA per SM (the table fills shared memory): all the warps it can hold
+__global__ void __launch_bounds__(GMS_THREADS)
+gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int N, int k, int Cout,
+                       int psplit, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ out_hi,
+                       float *__restrict__ out_lo)
+{
+    extern __shared__ float4 ptab[];                               // N rows x 8 float4
+    const int slices = Cout >> 5;
+    const int unit = blockIdx.x;
+    const int ps = unit % psplit, sl = (unit / psplit) % slices, cloud = unit / (psplit * slices);
+    const int64_t cloud0 = (int64_t)cloud * N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ptab);
+        for (int t = tid; t < N * 8; t += GMS_THREADS) {
+            const int j = t >> 3, q = t & 7;
+            const float *src = PQ + (cloud0 + j) * ldpq + sl * 32 + q * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)t * 16u), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int g = lane >> 3, q = lane & 7;                          // 4 points per warp instruction, 8 lanes each
+    const int per = N / psplit;
+    for (int p0 = ps * per + warp * 4; p0 < (ps + 1) * per; p0 += GMS_THREADS / 8) {
+        const int i = p0 + g;
+        const int32_t *row = idx + (cloud0 + i) * k;
+        const float4 qv = *reinterpret_cast<const float4 *>(PQ + (cloud0 + i) * ldpq + Cout + sl * 32 + q * 4);   // in flight early
+        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll 5
+        for (int t = 0; t < k; ++t) {
+            const float4 v = ptab[__ldg(row + t) * 8 + q];
+            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+        }
+        float4 r;
+        r.x = apply_act(mx.x + qv.x, act); r.y = apply_act(mx.y + qv.y, act);
+        r.z = apply_act(mx.z + qv.z, act); r.w = apply_act(mx.w + qv.w, act);
+        const int64_t o = (cloud0 + i) * ldo + sl * 32 + q * 4;
+        *reinterpret_cast<float4 *>(out + o) = r;
+        if (out_hi) {
+            float4 h, l;
+            h.x = __uint_as_float((__float_as_uint(r.x) + 0x1000u) & 0xffffe000u);
+            h.y = __uint_as_float((__float_as_uint(r.y) + 0x1000u) & 0xffffe000u);
+            h.z = __uint_as_float((__float_as_uint(r.z) + 0x1000u) & 0xffffe000u);
+            h.w = __uint_as_float((__float_as_uint(r.w) + 0x1000u) & 0xffffe000u);
+            l.x = __uint_as_float((__float_as_uint(r.x - h.x) + 0x1000u) & 0xffffe000u);
+            l.y = __uint_as_float((__float_as_uint(r.y - h.y) + 0x1000u) & 0xffffe000u);
+            l.z = __uint_as_float((__float_as_uint(r.z - h.z) + 0x1000u) & 0xffffe000u);
+            l.w = __uint_as_float((__float_as_uint(r.w - h.w) + 0x1000u) & 0xffffe000u);
+            *reinterpret_cast<float4 *>(out_hi + o) = h;
+            *reinterpret_cast<float4 *>(out_lo + o) = l;
+        }
+    }
+}
+
 __global__ void xyz_to_point_major_kernel(const float *__restrict__ cf, int N, float *__restrict__ pm)
 {
     const int b = blockIdx.y;
@@ -479,11 +539,31 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
                       int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,
                       cudaStream_t st)
 {
-    ProfileScope _ps("gather_max", st);
     const int64_t total = B * N;
     if (total == 0) return 0;
     IQ_CHECK(Cout == 64 || Cout == 128 || Cout == 256, "gather_max: Cout must be 64, 128 or 256");
     IQ_CHECK(ldpq % 4 == 0 && ldo % 4 == 0, "gather_max: leading dimensions must be multiples of 4");
+    const size_t smem = (size_t)N * 128;
+    if (smem <= 200 * 1024 && N % 128 == 0 && B * (Cout / 32) * 8 < ((int64_t)1 << 31)) {
+        {
+            ProfileScope _ps("gather_max", st);
+            static bool attr_set = false;
+            if (!attr_set) {
+                IQ_CUDA(cudaFuncSetAttribute(gather_max_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            const int64_t base_units = B * (Cout / 32);
+            int psplit = 1;
+            while (psplit < 4 && base_units * psplit < 120) psplit *= 2;   // fill the SMs, but keep the units fat
+            gather_max_smem_kernel<<<(unsigned)(base_units * psplit), GMS_THREADS, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
+                                                                                       act, out, ldo, out_hi, out_lo);
+            IQ_COUNT_LAUNCH();
+            IQ_LAUNCH_CHECK();
+        }
+        if (neg_sqnorm) return launch_sqnorm_rows(out, total, Cout, ldo, neg_sqnorm, st);
+        return 0;
+    }
+    ProfileScope _ps("gather_max", st);
     const unsigned grid = (unsigned)ceil_div(total * 32, 256);
     if (Cout == 64) gather_max_kernel<2><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
     else if (Cout == 128) gather_max_kernel<4><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
