@@ -365,31 +365,60 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
     }
 }
 
-__device__ __forceinline__ int warp_exclusive_scan(int x, int lane, int &total)
+
+// position of the r-th (0-based) set bit of m, by popcount bisection
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int r)
 {
-    int incl = x;
+    int pos = 0, t;
+    t = __popc(m & 0xffffu); if (r >= t) { r -= t; pos += 16; m >>= 16; }
+    t = __popc(m & 0xffu);   if (r >= t) { r -= t; pos += 8;  m >>= 8; }
+    t = __popc(m & 0xfu);    if (r >= t) { r -= t; pos += 4;  m >>= 4; }
+    t = __popc(m & 0x3u);    if (r >= t) { r -= t; pos += 2;  m >>= 2; }
+    if (r >= (int)(m & 1u)) pos += 1;
+    return pos;
+}
+
+// Every lane holds one mask word m (word w0 + lane) and the inclusive prefix count incl of set bits over the lanes.
+// Returns the column of the s-th set bit in word order (meaningless when s is out of range; all lanes must call).
+__device__ __forceinline__ int column_of_slot(uint32_t m, int incl, int s, int w0)
+{
+    int w = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(FULL, incl, w + step - 1);
+        if (v <= s) w += step;
+    }
+    w = min(w, 31);
+    const uint32_t mw = __shfl_sync(FULL, m, w);
+    const int before = __shfl_sync(FULL, incl - __popc(m), w);
+    return (w0 + w) * 32 + nth_set_bit(mw, s - before);
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int x, int lane)
+{
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += y;
+        const int y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
     }
-    total = __shfl_sync(FULL, incl, 31);
-    return incl - x;
+    return x;
 }
 
 // ---- exact decision among the candidates ------------------------------------------------------------------
-// One warp per row.  The masks are decoded into the warp's candidate list (index order).  LPC = C/16 lanes share a
-// candidate (each lane 16 channels as 4 float4, interleaved so a group reads 64 contiguous bytes per instruction), so
-// a warp evaluates 32/LPC candidates at a time; the usual case of <= 32 candidates is then ordered by a 15-step
-// bitonic network over the lanes, keyed by (float64 distance, index).
+// One warp per row.  The masks are decoded slot-parallel (lane s finds the s-th set bit by bisection over the prefix
+// counts: no per-bit loops, which the masked rows with their hundreds of ties would run 24 times).  LPC = C/16 lanes
+// share a candidate (each lane 16 channels as 4 float4, interleaved so a group reads 64 contiguous bytes per
+// instruction), so a warp evaluates 32/LPC candidates at a time with all loads of four such steps in flight; the usual
+// case of <= 32 candidates is then ordered by a 15-step bitonic network over the lanes, keyed by (float64 distance,
+// index).
 template <int C>
 __global__ void __launch_bounds__(256, 3)
 knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *__restrict__ masks, int64_t rows, int N,
                        int k, int32_t *__restrict__ idx, int32_t *__restrict__ cnt)
 {
     constexpr int LPC = C / 16;                                      // lanes per candidate: 4 (C = 64) or 8 (C = 128)
-    constexpr int CPI = 32 / LPC;                                    // candidates per iteration
-    constexpr int ITERS = 32 / CPI;                                  // iterations per batch of 32 candidates
+    constexpr int CPI = 32 / LPC;                                    // candidates per step
+    constexpr int ITERS = 32 / CPI;                                  // steps per batch of 32 candidates
     __shared__ uint16_t cand_s[8][KNN_CAND_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -397,33 +426,32 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
     const int words = N >> 5;
     const uint32_t *mg = masks + row * (int64_t)(2 * words), *me = mg + words;
     uint16_t *cl = cand_s[wib];
+    const int grp = lane / LPC, sub = lane % LPC;
+    float4 xi[4];                                                    // my 16 channels of the row itself, in flight early
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xi[q] = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + q * LPC + sub);
+
     int n = 0;
     for (int w0 = 0; w0 < words; w0 += 32) {                          // every column above the threshold
         const int w = w0 + lane;
         uint32_t m = w < words ? __ldg(mg + w) : 0u;
-        int tot;
-        int pos = n + warp_exclusive_scan(__popc(m), lane, tot);
-        while (m) {
+        const int incl = warp_inclusive_scan(__popc(m), lane);
+        int pos = n + incl - __popc(m);
+        while (m) {                                                  // ~1 bit per word
             const int b = __ffs(m) - 1;
             m &= m - 1;
             if (pos < KNN_CAND_CAP) cl[pos] = (uint16_t)(w * 32 + b);
             ++pos;
         }
-        n += tot;
+        n += __shfl_sync(FULL, incl, 31);
     }
     int need = KNN_NOM - n;                                            // then the lowest-index ties, up to NOM in all
     for (int w0 = 0; w0 < words && need > 0; w0 += 32) {
-        const int w = w0 + lane;
-        uint32_t m = w < words ? __ldg(me + w) : 0u;
-        int tot;
-        int e = warp_exclusive_scan(__popc(m), lane, tot);
-        while (m && e < need) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            cl[n + e] = (uint16_t)(w * 32 + b);                       // n + e < NOM <= capacity
-            ++e;
-        }
-        const int took = min(tot, need);
+        const uint32_t m = w0 + lane < words ? __ldg(me + w0 + lane) : 0u;
+        const int incl = warp_inclusive_scan(__popc(m), lane);
+        const int took = min(__shfl_sync(FULL, incl, 31), need);
+        const int col = column_of_slot(m, incl, lane, w0);
+        if (lane < took) cl[n + lane] = (uint16_t)col;               // n + lane < NOM <= capacity
         n += took;
         need -= took;
     }
@@ -431,10 +459,7 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
     if (n > KNN_CAND_CAP || n < k) return;                           // redone by knn_exact_rows_kernel
     __syncwarp();
     const int64_t cloud0 = (row / N) * N;
-    const int grp = lane / LPC, sub = lane % LPC;
-    float4 xi[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) xi[q] = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + q * LPC + sub);
+    const int self = (int)(row - cloud0);
     const int batches = n > 32 ? 2 : 1;
     double myd[2] = {INFINITY, INFINITY};
     int myj[2] = {0x7fffffff, 0x7fffffff};
@@ -443,24 +468,31 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
         if (bt >= batches) break;
         double dacc[ITERS];
 #pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int slot = bt * 32 + it * CPI + grp;
-            double acc = 0.0;
-            if (slot < n) {
-                const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + cl[slot]) * ld);
+        for (int i0 = 0; i0 < ITERS; i0 += 2) {                      // two steps' worth of loads in flight
+            float4 b[2][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 b = __ldg(xj + q * LPC + sub);
-                    const double d0 = (double)(xi[q].x - b.x), d1 = (double)(xi[q].y - b.y);
-                    const double d2 = (double)(xi[q].z - b.z), d3 = (double)(xi[q].w - b.w);
-                    acc = fma(d0, d0, acc); acc = fma(d1, d1, acc); acc = fma(d2, d2, acc); acc = fma(d3, d3, acc);
-                }
+            for (int u = 0; u < 2; ++u) {
+                const int slot = bt * 32 + (i0 + u) * CPI + grp;
+                const int j = slot < n ? (int)cl[slot] : self;       // unconditional loads: out-of-range slots read the row itself
+                const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) b[u][q] = __ldg(xj + q * LPC + sub);
             }
 #pragma unroll
-            for (int o = LPC / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            dacc[it] = acc;
+            for (int u = 0; u < 2; ++u) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double d0 = (double)(xi[q].x - b[u][q].x), d1 = (double)(xi[q].y - b[u][q].y);
+                    const double d2 = (double)(xi[q].z - b[u][q].z), d3 = (double)(xi[q].w - b[u][q].w);
+                    acc = fma(d0, d0, acc); acc = fma(d1, d1, acc); acc = fma(d2, d2, acc); acc = fma(d3, d3, acc);
+                }
+#pragma unroll
+                for (int o = LPC / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+                dacc[i0 + u] = acc;
+            }
         }
-        // candidate slot bt*32 + L moves to lane L: it was evaluated in iteration L / CPI by group L % CPI
+        // candidate slot bt*32 + L moves to lane L: it was evaluated in step L / CPI by group L % CPI
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const double v = __shfl_sync(FULL, dacc[it], (lane % CPI) * LPC);
@@ -469,22 +501,22 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
         if (bt * 32 + lane < n) myj[bt] = cl[bt * 32 + lane];
         else myd[bt] = INFINITY;
     }
-    // the reduction order above is fixed, so coincident points give bit-equal distances and fall back to the index
+    // The reduction order above is fixed, so coincident points give bit-equal distances and fall back to the index.
+    // Sort key: the bit pattern of a non-negative double orders like an integer; its 11 lowest mantissa bits (4.5e-13
+    // relative, far below the 6e-8 rounding of the fp32 differences) make room for the point index as the tie-break.
     if (batches == 1) {
-        double d = myd[0];
-        int j = myj[0];
+        unsigned long long key = ((unsigned long long)__double_as_longlong(myd[0]) & ~0x7ffull) | (unsigned)(myj[0] & 0x7ff);
+        if (lane >= n) key = ~0ull;
 #pragma unroll
         for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                const double od = __shfl_xor_sync(FULL, d, jj);
-                const int oj = __shfl_xor_sync(FULL, j, jj);
-                const bool other_first = od < d || (od == d && oj < j);
-                const bool want_first = ((lane & kk) == 0) == ((lane & jj) == 0);   // this lane keeps the smaller key
-                if (other_first == want_first) { d = od; j = oj; }
+                const unsigned long long other = __shfl_xor_sync(FULL, key, jj);
+                const bool keep_min = ((lane & kk) == 0) == ((lane & jj) == 0);
+                key = keep_min ? min(key, other) : max(key, other);
             }
         }
-        if (lane < k) idx[row * k + lane] = j;
+        if (lane < k) idx[row * k + lane] = (int)(key & 0x7ff);
         return;
     }
     int rank0 = 0, rank1 = 0;
