@@ -179,7 +179,7 @@ int iq_knn_features(const float *x, int64_t B, int64_t N, int64_t C, int k, int3
     uint32_t *cand = reinterpret_cast<uint32_t *>(cnt + rows);
     int rc = launch_split_tf32(x, rows, (int)C, C, hi, lo, C, st);
     if (!rc) rc = launch_sqnorm_rows(x, rows, (int)C, C, nxx, st);
-    if (!rc) rc = launch_knn_features_tc(x, hi, lo, C, (int)C, nxx, B, N, k, cand, cnt, idx, st);
+    if (!rc) rc = launch_knn_features_tc(x, hi, lo, C, (int)C, nxx, 1, B, N, k, cand, cnt, idx, st);
     if (!rc && cand_count && cudaMemcpyAsync(cand_count, cnt, sizeof(int32_t) * rows, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         rc = -2;
     cudaStreamSynchronize(st);

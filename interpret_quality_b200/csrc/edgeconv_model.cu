@@ -68,7 +68,7 @@ protected:
         uint32_t *cand = tc_knn ? ws.take<uint32_t>(rows * 2 * (N / 32)) : nullptr;
         int32_t *cnt = tc_knn ? ws.take<int32_t>(rows) : nullptr;
         float *feat = ws.take<float>(rows * 512);
-        float *nxx = ws.take<float>(rows);
+        float *nxx = ws.take<float>(rows * 4);          // squared norms of the layer just written, in up to 4 partial sums
         float *pq = ws.take<float>(rows * 512);
         float *feat_hi = tc ? ws.take<float>(rows * 512) : nullptr;
         float *feat_lo = tc ? ws.take<float>(rows * 512) : nullptr;
@@ -85,6 +85,7 @@ protected:
             pts = xyz;
         }
         if (int rc = launch_knn_xyz(pts, 1, Bc, N, k, idx, st)) return rc;
+        int nxx_parts = 1;
         for (int l = 0; l < 4; ++l) {
             const EdgeLayer &L = layers[l];
             const float *in = l == 0 ? pts : feat + layers[l - 1].col;
@@ -96,7 +97,7 @@ protected:
             // Downstream-only products (last EdgeConv, conv5) and GCNN run on tcgen05 3xTF32.
             if (l > 0 && tc_knn) {
                 if (int rc = launch_knn_features_tc(in, feat_hi + layers[l - 1].col, feat_lo + layers[l - 1].col, 512,
-                                                    L.cin, nxx, Bc, N, k, cand, cnt, idx, st))
+                                                    L.cin, nxx, nxx_parts, Bc, N, k, cand, cnt, idx, st))
                     return rc;
             } else if (l > 0 && dynamic) {
                 GemmDesc d;
@@ -122,7 +123,8 @@ protected:
                 if (int rc = launch_sgemm(p, st)) return rc;
             }
             if (int rc = launch_gather_max(pq, 2 * L.cout, idx, Bc, N, k, L.cout, ACT_LRELU, feat + L.col, 512,
-                                           (dynamic && l < 3) ? nxx : nullptr, tc ? feat_hi + L.col : nullptr,
+                                           (dynamic && l < 3) ? nxx : nullptr, tc_knn ? &nxx_parts : nullptr,
+                                           tc ? feat_hi + L.col : nullptr,
                                            tc ? feat_lo + L.col : nullptr, st))
                 return rc;
         }
@@ -154,7 +156,7 @@ Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int
     m->dynamic = dynamic_graph;
     m->k = k;
     m->num_classes = num_classes;
-    m->chunk = 32;
+    m->chunk = 148;              // 148 clouds x 8 row tiles = 8 full waves of the persistent tensor-core kernels
     const int cin[4] = {3, 64, 64, 128}, cout[4] = {64, 64, 128, 256}, col[4] = {0, 64, 128, 256};
     for (int l = 0; l < 4; ++l) {
         std::vector<float> w, b;

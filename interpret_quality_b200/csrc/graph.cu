@@ -385,7 +385,7 @@ constexpr int GMS_THREADS = 1024;             // one CTA per SM (the table fills
 __global__ void __launch_bounds__(GMS_THREADS)
 gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int N, int k, int Cout,
                        int psplit, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ out_hi,
-                       float *__restrict__ out_lo)
+                       float *__restrict__ out_lo, float *__restrict__ sq_part)
 {
     extern __shared__ float4 ptab[];                               // N rows x 8 float4
     const int slices = Cout >> 5;
@@ -432,6 +432,14 @@ gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t
             l.w = __uint_as_float((__float_as_uint(r.w - h.w) + 0x1000u) & 0xffffe000u);
             *reinterpret_cast<float4 *>(out_hi + o) = h;
             *reinterpret_cast<float4 *>(out_lo + o) = l;
+        }
+        if (sq_part) {                                              // this slice's share of |x_i|^2 (fixed summation order)
+            float ss = r.x * r.x;
+            ss = fmaf(r.y, r.y, ss); ss = fmaf(r.z, r.z, ss); ss = fmaf(r.w, r.w, ss);
+            ss += __shfl_xor_sync(FULL, ss, 4);
+            ss += __shfl_xor_sync(FULL, ss, 2);
+            ss += __shfl_xor_sync(FULL, ss, 1);
+            if (q == 0) sq_part[(cloud0 + i) * slices + sl] = ss;
         }
     }
 }
@@ -536,9 +544,10 @@ int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *o
 }
 
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
-                      int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,
+                      int act, float *out, int64_t ldo, float *neg_sqnorm, int *sq_parts, float *out_hi, float *out_lo,
                       cudaStream_t st)
 {
+    if (sq_parts) *sq_parts = 1;
     const int64_t total = B * N;
     if (total == 0) return 0;
     IQ_CHECK(Cout == 64 || Cout == 128 || Cout == 256, "gather_max: Cout must be 64, 128 or 256");
@@ -555,12 +564,15 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
             const int64_t base_units = B * (Cout / 32);
             int psplit = 1;
             while (psplit < 4 && base_units * psplit < 120) psplit *= 2;   // fill the SMs, but keep the units fat
+            // the caller can take per-slice partial squared norms (sq_parts != null: |x_i|^2 = sum of Cout/32 parts)
+            float *parts = (neg_sqnorm && sq_parts) ? neg_sqnorm : nullptr;
             gather_max_smem_kernel<<<(unsigned)(base_units * psplit), GMS_THREADS, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
-                                                                                       act, out, ldo, out_hi, out_lo);
+                                                                                       act, out, ldo, out_hi, out_lo, parts);
             IQ_COUNT_LAUNCH();
             IQ_LAUNCH_CHECK();
+            if (parts) *sq_parts = Cout / 32;
         }
-        if (neg_sqnorm) return launch_sqnorm_rows(out, total, Cout, ldo, neg_sqnorm, st);
+        if (neg_sqnorm && !sq_parts) return launch_sqnorm_rows(out, total, Cout, ldo, neg_sqnorm, st);
         return 0;
     }
     ProfileScope _ps("gather_max", st);

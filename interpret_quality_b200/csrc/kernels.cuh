@@ -83,10 +83,11 @@ int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float
 // knn_tc.cu -- fused tcgen05 Gram + candidate selection + exact re-rank (feature-space kNN of DGCNN)
 constexpr int KNN_CAND_CAP = 64;      // most candidates per row the re-rank handles
 bool knn_features_tc_supported(int64_t N, int C, int k);
-// x (clouds*N, C) fp32 with leading dimension ld, x_hi / x_lo its tf32 split (same ld), nxx = -|x_j|^2 per row;
+// x (clouds*N, C) fp32 with leading dimension ld, x_hi / x_lo its tf32 split (same ld); nxx (rows, nxx_parts): the
+// squared norm of row j is |sum_p nxx[j][p]| (one negated value, or positive partial sums);
 // scratch: masks (rows, 2, N/32) u32, cnt (rows) i32; out idx (rows, k) sorted by (distance, index)
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
-                           int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
+                           int nxx_parts, int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
                            cudaStream_t st);
 
 // graph.cu
@@ -98,8 +99,10 @@ int launch_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int
 int launch_knn_rerank(const float *x, int64_t ld, int C, const int32_t *cand, int64_t rows, int64_t N, int k,
                       int32_t *idx, cudaStream_t st);
 int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st);
+// neg_sqnorm (optional): -|out_i|^2 per row; when sq_parts is given the kernel may instead leave *sq_parts positive
+// partial sums per row, (rows, *sq_parts), whose total is |out_i|^2 (buffer of rows * Cout/32 floats)
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
-                      int act, float *out, int64_t ldo, float *neg_sqnorm, float *out_hi, float *out_lo,
+                      int act, float *out, int64_t ldo, float *neg_sqnorm, int *sq_parts, float *out_hi, float *out_lo,
                       cudaStream_t st);
 int launch_xyz_to_point_major(const float *x_cf, int64_t B, int64_t N, float *x_pm, cudaStream_t st);
 

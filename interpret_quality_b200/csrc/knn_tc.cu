@@ -53,7 +53,8 @@ struct KnnParams {
     int num_units;         // clouds * m_tiles
     const float *x_hi, *x_lo;   // tf32 split of the features, leading dimension ld (the A rows are read directly)
     int64_t ld;
-    const float *nxx;      // (rows) -|x_j|^2
+    const float *nxx;      // (rows, nxx_parts): |x_j|^2 = |sum of the parts|
+    int nxx_parts;
     uint32_t *masks;       // (rows, 2, N/32): bit j of [row][0] <=> key > T0, of [row][1] <=> key == T0
     int dbg;               // IQ_KNN_DBG (scripts/knn_probe.py): 1 = epilogue skips its math, 2 = no MMAs, 4 = no TMA loads
 };
@@ -257,7 +258,12 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
                 if (lane == 0) mbar_arrive(a_full);
             }
             epi_bar_sync();                                          // everyone is done with the previous unit's smem
-            for (int i = etid; i < p.points; i += KNN_EPI_THREADS) nb[i] = __ldg(p.nxx + cloud_row0 + i);
+            for (int i = etid; i < p.points; i += KNN_EPI_THREADS) {
+                const float *src = p.nxx + (cloud_row0 + i) * p.nxx_parts;
+                float sum = __ldg(src);
+                for (int q = 1; q < p.nxx_parts; ++q) sum += __ldg(src + q);
+                nb[i] = -fabsf(sum);
+            }
             epi_bar_sync();
 
             // ---- sweep 1: running maxima of this half's strided column blocks (column j -> block j mod HC)
@@ -605,7 +611,7 @@ bool knn_features_tc_supported(int64_t N, int C, int k)
 }
 
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
-                           int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
+                           int nxx_parts, int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
                            cudaStream_t st)
 {
     IQ_CHECK(knn_features_tc_supported(N, C, k), "knn_features_tc: unsupported shape");
@@ -615,7 +621,7 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
     IQ_CHECK(rows < (int64_t)1 << 31, "knn_features_tc: too many rows");
     KnnParams p;
     p.K = C; p.points = (int)N; p.m_tiles = (int)(N / TBM); p.num_units = (int)(clouds * p.m_tiles);
-    p.nxx = nxx; p.masks = masks; p.x_hi = x_hi; p.x_lo = x_lo; p.ld = ld;
+    p.nxx = nxx; p.nxx_parts = nxx_parts; p.masks = masks; p.x_hi = x_hi; p.x_lo = x_lo; p.ld = ld;
     const char *dbg = getenv("IQ_KNN_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
     {

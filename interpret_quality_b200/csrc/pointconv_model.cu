@@ -418,7 +418,7 @@ Model *create_pointconv_model(const StateDict &sd, int num_classes, std::string 
 {
     std::unique_ptr<PointConvModel> m(new PointConvModel());
     m->num_classes = num_classes;
-    m->chunk = 16;
+    m->chunk = 330;
     PointConvModel *p = m.get();
     const int m1[3] = {64, 64, 128}, m2[3] = {128, 128, 256}, m3[3] = {256, 512, 1024};
     const bool ok = make_sa(p, sd, "sa1", 512, 32, 0, m1, 0.1, false, m->sa[0], err) &&

@@ -224,7 +224,7 @@ Model *create_pointnet2_model(const StateDict &sd, int num_classes, std::string 
 {
     std::unique_ptr<PointNet2Model> m(new PointNet2Model());
     m->num_classes = num_classes;
-    m->chunk = 8;
+    m->chunk = 165;
     PointNet2Model *p = m.get();
     const double r1[3] = {0.1, 0.2, 0.4}, r2[3] = {0.2, 0.4, 0.8};
     const int k1[3] = {16, 32, 128}, k2[3] = {32, 64, 128};
