@@ -172,19 +172,44 @@ __device__ __forceinline__ float reward_of_row(const float *z, int C, int lbl, i
     return softmax_normal ? (z[lbl] - mx) - logf(s) : z[lbl] - (logf(s) + mx);
 }
 
+// A row of logits is 40 bytes (160 for the 4 clouds of a context): read one row per thread, a warp touches 10-40 lines per
+// load instruction and L1 throughput, not HBM, bounds the kernel.  The block's rows are contiguous, so they are copied
+// with coalesced loads into shared memory (row stride odd: conflict-free) and evaluated from there.
+__device__ __forceinline__ void stage_rows(const float *__restrict__ src, int64_t first_row, int64_t total_rows, int row_len,
+                                           float *smem)
+{
+    const int rows = (int)min((int64_t)blockDim.x, total_rows - first_row);
+    const float *base = src + first_row * row_len;
+    const int n = rows * row_len, stride = row_len | 1;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int r = t / row_len, c = t - r * row_len;
+        smem[r * stride + c] = __ldg(base + t);
+    }
+    __syncthreads();
+}
+
 __global__ void reward_kernel(const float *__restrict__ logits, int64_t B, int C, int lbl, int softmax_normal,
                               float *__restrict__ v)
 {
-    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (b < B) v[b] = reward_of_row(logits + b * C, C, lbl, softmax_normal);
+    extern __shared__ float rows_s[];
+    const int64_t first = blockIdx.x * (int64_t)blockDim.x;
+    stage_rows(logits, first, B, C, rows_s);
+    const int64_t b = first + threadIdx.x;
+    if (b < B) v[b] = reward_of_row(rows_s + threadIdx.x * (C | 1), C, lbl, softmax_normal);
 }
 
 int launch_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v, cudaStream_t st)
 {
     ProfileScope _ps("reward", st);
-    IQ_CHECK(C >= 2 && lbl >= 0 && lbl < C, "reward: label out of range");
+    IQ_CHECK(C >= 2 && C <= 256 && lbl >= 0 && lbl < C, "reward: label out of range");
     if (B == 0) return 0;
-    reward_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, st>>>(logits, B, (int)C, (int)lbl, softmax_normal, v);
+    const size_t smem = sizeof(float) * 128 * (size_t)(C | 1);
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        IQ_CUDA(cudaFuncSetAttribute(reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    reward_kernel<<<(unsigned)ceil_div(B, 128), 128, smem, st>>>(logits, B, (int)C, (int)lbl, softmax_normal, v);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -237,6 +262,8 @@ int launch_shapley_accumulate(const float *v, const int64_t *orders, int64_t bs,
 // ------------------------------------------------------------------ interaction score
 // out[p][k] = double((v[4k] + v[4k+3]) - v[4k+1] - v[4k+2]) with the fp32
 // operation order of final_cal_interactions.py:33.
+// 40 expf + 4 logf per context against 168 bytes: bound by the SFU / ALU work of the exact softmax, not by HBM
+// (staging the rows in shared memory like reward_kernel measured no gain).
 __global__ void interaction_reduce_kernel(const float *__restrict__ logits, int64_t total, int C, int lbl,
                                           int softmax_normal, double *__restrict__ out)
 {

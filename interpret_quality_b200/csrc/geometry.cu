@@ -70,13 +70,11 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, int64_t *__restrict
         const int buf = s & 1;
         if (lane == 0) { wbest[buf][warp] = wmax; warg[buf][warp] = wmin; }
         __syncthreads();
-        int gb = wbest[buf][0], ga = warg[buf][0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) {
-            const int vb = wbest[buf][w], va = warg[buf][w];
-            if (vb > gb || (vb == gb && va < ga)) { gb = vb; ga = va; }
-        }
-        far = ga;
+        // combine the 8 warp results: lanes 0-7 take one each, two more REDUX (largest distance, lowest index on ties)
+        const int vb = lane < 8 ? wbest[buf][lane] : -1;
+        const int va = lane < 8 ? warg[buf][lane] : INT_MAX;
+        const int gb = __reduce_max_sync(0xffffffffu, vb);
+        far = __reduce_min_sync(0xffffffffu, vb == gb ? va : INT_MAX);
     }
 }
 
