@@ -537,47 +537,50 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
 }
 
 // ---- exhaustive redo of a row (overflowed or short candidate set): k rounds of "nearest point after the previous
-// pick" under (float64 distance, index).  O(k N C) per row, slow and normally never taken.
+// pick" under (float64 distance, index).  O(k N C) per row, slow and normally never taken: a small grid scans the
+// candidate counts 32 rows per warp step and only stops at flagged rows.
 __global__ void __launch_bounds__(256)
 knn_exact_rows_kernel(const float *__restrict__ x, int64_t ld, int C, const int32_t *__restrict__ cnt, int64_t rows,
                       int N, int k, int32_t *__restrict__ idx)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= rows) return;
-    const int n = cnt[row];
-    if (!(n > KNN_CAND_CAP || n < k)) return;
-    const int64_t cloud0 = (row / N) * N;
-    const float4 *xi = reinterpret_cast<const float4 *>(x + row * ld);
-    auto dist = [&](int j) {
-        const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
-        double acc = 0.0;
-        for (int c = 0; c < (C >> 2); ++c) {
-            const float4 a = __ldg(xi + c), b = __ldg(xj + c);
-            const double d0 = (double)(a.x - b.x), d1 = (double)(a.y - b.y), d2 = (double)(a.z - b.z), d3 = (double)(a.w - b.w);
-            acc = fma(d0, d0, acc); acc = fma(d1, d1, acc); acc = fma(d2, d2, acc); acc = fma(d3, d3, acc);
-        }
-        return acc;
-    };
-    double last_d = -1.0;
-    int last_j = -1;
-    for (int r = 0; r < k; ++r) {
-        double best_d = INFINITY;
-        int best_j = 0x7fffffff;
-        for (int j = lane; j < N; j += 32) {
-            const double d = dist(j);
-            const bool after = d > last_d || (d == last_d && j > last_j);
-            if (after && (d < best_d || (d == best_d && j < best_j))) { best_d = d; best_j = j; }
-        }
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp * 32; r0 < rows; r0 += nwarps * 32) {
+        const int n = r0 + lane < rows ? __ldg(cnt + r0 + lane) : k;
+        unsigned todo = __ballot_sync(FULL, n > KNN_CAND_CAP || n < k);
+        while (todo) {
+            const int64_t row = r0 + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t cloud0 = (row / N) * N;
+            const float4 *xi = reinterpret_cast<const float4 *>(x + row * ld);
+            double last_d = -1.0;
+            int last_j = -1;
+            for (int r = 0; r < k; ++r) {
+                double best_d = INFINITY;
+                int best_j = 0x7fffffff;
+                for (int j = lane; j < N; j += 32) {
+                    const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
+                    double d = 0.0;
+                    for (int c = 0; c < (C >> 2); ++c) {
+                        const float4 a = __ldg(xi + c), b = __ldg(xj + c);
+                        const double d0 = (double)(a.x - b.x), d1 = (double)(a.y - b.y), d2 = (double)(a.z - b.z), d3 = (double)(a.w - b.w);
+                        d = fma(d0, d0, d); d = fma(d1, d1, d); d = fma(d2, d2, d); d = fma(d3, d3, d);
+                    }
+                    const bool after = d > last_d || (d == last_d && j > last_j);
+                    if (after && (d < best_d || (d == best_d && j < best_j))) { best_d = d; best_j = j; }
+                }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(FULL, best_d, o);
-            const int oj = __shfl_xor_sync(FULL, best_j, o);
-            if (od < best_d || (od == best_d && oj < best_j)) { best_d = od; best_j = oj; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(FULL, best_d, o);
+                    const int oj = __shfl_xor_sync(FULL, best_j, o);
+                    if (od < best_d || (od == best_d && oj < best_j)) { best_d = od; best_j = oj; }
+                }
+                if (lane == 0) idx[row * k + r] = best_j;
+                last_d = best_d;
+                last_j = best_j;
+            }
         }
-        if (lane == 0) idx[row * k + r] = best_j;
-        last_d = best_d;
-        last_j = best_j;
     }
 }
 
@@ -637,7 +640,8 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
         else knn_rerank_mask_kernel<128><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
         IQ_COUNT_LAUNCH();
         IQ_LAUNCH_CHECK();
-        knn_exact_rows_kernel<<<grid, 256, 0, st>>>(x, ld, C, cnt, rows, (int)N, k, idx);
+        const unsigned scan_grid = (unsigned)std::min<int64_t>(ceil_div(rows, 32 * 8), 4 * sm_count());
+        knn_exact_rows_kernel<<<scan_grid, 256, 0, st>>>(x, ld, C, cnt, rows, (int)N, k, idx);
         IQ_COUNT_LAUNCH();
         IQ_LAUNCH_CHECK();
     }
