@@ -65,8 +65,9 @@ struct KnnSmem {
     static constexpr int STAGE_BYTES = 2 * B_TILE;
     static constexpr int NB_BYTES = 2048 * 4;
     static constexpr int XCH_BYTES = 2 * TBM * XCH_STRIDE * 4;
+    static constexpr int XPOSE_BYTES = 8 * 4096;                   // per epilogue warp: 32 rows x 128 B transpose tile
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + NB_BYTES + XCH_BYTES + BAR_BYTES + 1024;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + XPOSE_BYTES + NB_BYTES + XCH_BYTES + BAR_BYTES + 1024;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -109,7 +110,8 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *b_smem = smem;
-    float *nb = reinterpret_cast<float *>(b_smem + STAGES * S::STAGE_BYTES);
+    uint8_t *a_xpose = b_smem + STAGES * S::STAGE_BYTES;            // 1 KB aligned: stages are multiples of 1 KB
+    float *nb = reinterpret_cast<float *>(a_xpose + S::XPOSE_BYTES);
     float *xch = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(nb) + S::NB_BYTES);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(xch) + S::XCH_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
@@ -234,22 +236,43 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
             const int cloud = unit / p.m_tiles, mt = unit - cloud * p.m_tiles;
             const int64_t cloud_row0 = (int64_t)cloud * p.points;
             const int64_t row = cloud_row0 + mt * TBM + row_in_tile;
-            // ---- park this unit's A rows in TMEM: half 0 writes the hi part of its row, half 1 the lo part
+            // ---- park this unit's A rows in TMEM: half 0 writes the hi part of its rows, half 1 the lo part.  A thread
+            // reading its own row touches 32 lines per load instruction (measured: ~8 k clk per unit with the tensor
+            // pipe idle), so each warp loads its 32 rows coalesced (4 rows x 128 B per instruction), transposes them
+            // through a 128B-swizzled 4 KB tile of shared memory and only then takes one row per lane.
             {
-                const float4 *src = reinterpret_cast<const float4 *>((half ? p.x_lo : p.x_hi) + row * p.ld);
+                const float *src = (half ? p.x_lo : p.x_hi) + (cloud_row0 + mt * TBM + quad * 32) * p.ld;
                 const uint32_t a_t = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL + (uint32_t)(half * KMAX);
+                const uint32_t stg = smem_u32(a_xpose) + (uint32_t)(warp - 2) * 4096u;
+                const int lr = lane >> 3, lq = lane & 7;
+                float4 g[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    g[it] = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(it * 4 + lr) * p.ld) + lq);
                 mbar_wait(a_empty, a_phase ^ 1);                     // MMAs of the previous unit have retired
                 a_phase ^= 1;
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < KMAX / 32; ++c) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + lr;
+                        sts128(stg + (uint32_t)r * 128u + (uint32_t)((lq ^ (r & 7)) << 4), g[it].x, g[it].y, g[it].z, g[it].w);
+                    }
+                    __syncwarp();
+                    if (c + 1 < KMAX / 32) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)
+                            g[it] = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(it * 4 + lr) * p.ld) + (c + 1) * 8 + lq);
+                    }
                     uint32_t r[32];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 f = __ldg(src + c * 8 + q);
+                        const float4 f = lds128(stg + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4));
                         r[4 * q] = __float_as_uint(f.x); r[4 * q + 1] = __float_as_uint(f.y);
                         r[4 * q + 2] = __float_as_uint(f.z); r[4 * q + 3] = __float_as_uint(f.w);
                     }
+                    __syncwarp();
                     tmem_st32(a_t + 32 * c, r);
                 }
                 tmem_st_wait();
@@ -629,8 +652,8 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
     p.dbg = dbg ? atoi(dbg) : 0;
     {
         ProfileScope _ps(C <= 64 ? "tc_gram_knn_c64" : "tc_gram_knn_c128", st);
-        int rc = C == 64 ? launch_variant<128, 6, 64>(x_hi, x_lo, ld, rows, p, st)
-                         : launch_variant<128, 6, 128>(x_hi, x_lo, ld, rows, p, st);
+        int rc = C == 64 ? launch_variant<128, 5, 64>(x_hi, x_lo, ld, rows, p, st)
+                         : launch_variant<128, 5, 128>(x_hi, x_lo, ld, rows, p, st);
         if (rc) return rc;
     }
     {
