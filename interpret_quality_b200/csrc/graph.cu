@@ -81,6 +81,21 @@ __device__ __forceinline__ uint32_t warp_select_rank(uint32_t u, int r, int lane
     return res;
 }
 
+// descending bitonic sort of one 32-bit key per lane
+__device__ __forceinline__ uint32_t warp_sort_desc(uint32_t u, int lane)
+{
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            const uint32_t o = __shfl_xor_sync(FULL, u, jj);
+            const bool keep_max = ((lane & kk) == 0) == ((lane & jj) == 0);
+            u = keep_max ? max(u, o) : min(u, o);
+        }
+    }
+    return u;
+}
+
 template <int V>
 __device__ __forceinline__ void warp_topk(const float (&key)[V], int k, int lane, int32_t *out, float *scratch)
 {
@@ -88,29 +103,33 @@ __device__ __forceinline__ void warp_topk(const float (&key)[V], int k, int lane
     float T = 0.0f;
     bool have = false;
     if (k <= 32) {
-        float m = key[0];
+        // 64 block maxima (two per lane), each half sorted over the lanes by a 15-step bitonic network; the k-th
+        // largest of the union of two descending lists a, b is min_i max(a[i], b[k-1-i]): at least k keys are >= T0
+        float ma = key[0], mb = key[V / 2];
 #pragma unroll
-        for (int v = 1; v < V; ++v) m = fmaxf(m, key[v]);
-        // k-th largest lane maximum: at least k keys are >= T0
-        const float T0 = from_ordered_u32(warp_select_rank(ordered_u32(m), k - 1, lane));
+        for (int v = 1; v < V / 2; ++v) { ma = fmaxf(ma, key[v]); mb = fmaxf(mb, key[V / 2 + v]); }
+        const uint32_t sa = warp_sort_desc(ordered_u32(ma), lane);
+        const uint32_t sb = warp_sort_desc(ordered_u32(mb), lane);
+        const uint32_t bo = __shfl_sync(FULL, sb, (k - 1 - lane) & 31);
+        const float T0 = from_ordered_u32(__reduce_min_sync(FULL, lane < k ? max(sa, bo) : 0xffffffffu));
         mask_t mg = 0;
 #pragma unroll
         for (int v = 0; v < V; ++v) mg |= (mask_t)(key[v] > T0 ? 1 : 0) << v;
         const int g = mask_popc(mg);
         const int G = __reduce_add_sync(FULL, g);
         if (G < k) {
-            T = T0;
+            T = T0;                                                // fewer than k above T0, at least k at or above it
             have = true;
         } else if (G <= 32) {
-            // the k-th largest key is among the G keys above T0: one per lane, then rank select again
+            // the k-th largest key is among the G keys above T0: one per lane, sorted, rank k-1
             const int off = warp_exclusive_scan(g, lane);
             int w = off;
 #pragma unroll
             for (int v = 0; v < V; ++v)
                 if ((mg >> v) & 1) scratch[w++] = key[v];
             __syncwarp();
-            const uint32_t c = lane < G ? ordered_u32(scratch[lane]) : 0u;
-            T = from_ordered_u32(warp_select_rank(c, k - 1, lane));
+            const uint32_t c = warp_sort_desc(lane < G ? ordered_u32(scratch[lane]) : 0u, lane);
+            T = from_ordered_u32(__shfl_sync(FULL, c, k - 1));
             have = true;
             __syncwarp();
         }
