@@ -10,6 +10,8 @@
 //             PQ   = X [s*Wa ; s*(Wb-Wa)]^T + [0 ; t]    (GEMM)
 //             X_l  = lrelu(max_j P[idx] + Q)             (gather_max) -> column slice of the 512-wide concat
 //   conv5 + BN + lrelu with fused max / mean pooling over the points, then the 3-layer head.
+#include <stdlib.h>
+
 #include "model.cuh"
 
 namespace iq {
@@ -109,7 +111,8 @@ protected:
                 if (int rc = launch_sgemm(d, st)) return rc;
                 if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
             }
-            if (l > 0 && tc && (!dynamic || l == 3)) {
+            static const bool tc_all = getenv("IQ_TC_ALL") != nullptr;   // experiment: EdgeConv 2-3 P|Q on tcgen05 too
+            if (l > 0 && tc && (!dynamic || l == 3 || tc_all)) {
                 TcGemm p;
                 p.A_hi = feat_hi + layers[l - 1].col; p.A_lo = feat_lo + layers[l - 1].col; p.lda = 512;
                 p.B_hi = L.wcat_hi; p.B_lo = L.wcat_lo; p.ldb = L.cin;

@@ -429,10 +429,25 @@ gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t
         const int32_t *row = idx + (cloud0 + i) * k;
         const float4 qv = *reinterpret_cast<const float4 *>(PQ + (cloud0 + i) * ldpq + Cout + sl * 32 + q * 4);   // in flight early
         float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll 5
-        for (int t = 0; t < k; ++t) {
-            const float4 v = ptab[__ldg(row + t) * 8 + q];
-            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+        if (k == 20) {                                              // the whole neighbour list in five 16-byte loads
+            int4 nb[5];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) nb[t] = __ldg(reinterpret_cast<const int4 *>(row) + t);
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const int js[4] = {nb[t].x, nb[t].y, nb[t].z, nb[t].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 v = ptab[js[e] * 8 + q];
+                    mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int t = 0; t < k; ++t) {
+                const float4 v = ptab[__ldg(row + t) * 8 + q];
+                mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+            }
         }
         float4 r;
         r.x = apply_act(mx.x + qv.x, act); r.y = apply_act(mx.y + qv.y, act);
