@@ -1,6 +1,6 @@
 """The coalition engine behind the reference's call signatures
 (tools/final_common.py of ada-shen/Interpret_quality): get_reward :11-24, cal_reward :26-43,
-mask_data_batch :46-61, shap_sampling_all_regions_batch :64-103.
+mask_data_batch :46-61, shap_sampling_all_regions_batch :64-103, test (pose-enumeration runner) :107-174.
 
 Everything that computes runs in libiq_b200.so; this file only moves arguments.  Inputs may be
 host tensors / numpy arrays (they are copied to the model's device here, which is what bench.py's
@@ -88,3 +88,79 @@ def shap_sampling_all_regions_batch(model, data_disturb, lbl, region_id, load_or
     region_shap_value = phi_sum.cpu().numpy() / args.num_samples
     assert logits.shape[0] == args.num_samples * (args.num_regions + 1)
     return region_shap_value, logits
+
+
+def test(args, get_transform_params_fn, disturb_fn, print_info_fn, save_info_fn, samples=None, model=None):
+    """Pose-enumeration runner (tools/final_common.py:107-174 of the reference): for every cloud the Shapley
+    values of its regions at the original pose and at every enumerated pose (216 translations / rotations,
+    30 scales), written in the reference's files under <exp_folder>/<folder>/<mode>_all/:
+    orig_shapley_value.npy (R,), region_shapley_value.npy (poses,R) float64, all_logits.pt
+    (poses, num_samples*(R+1), C) float32, plus save_info_fn's pose parameters and log.txt.
+
+    The reference iterates its ModelNet / ShapeNet loaders; datasets are not part of this package, so the
+    clouds come from `samples`: an iterable of (data (1,N,3) tensor, lbl (1,) tensor, folder_name) whose
+    folders already hold norm_factor.npy, region_id.npy and all_orders.npy (final_shapley_value.py writes them).
+    `model` defaults to load_model(args).
+
+    Poses are a second independent axis: under torch.distributed the poses of a cloud are
+    dealt round-robin to the ranks, each rank runs whole poses, and the (poses,R) values and the logits are
+    combined by one allreduce of disjoint zero-initialised slabs; rank 0 writes the files."""
+    import time
+    import torch.distributed as dist
+    from .final_util import IOStream, load_model, mkdir
+    if samples is None:
+        raise ValueError("test(): pass samples=[(data, lbl, folder_name), ...]; the reference's dataset loaders "
+                         "are outside the scope of interpret_quality_b200")
+    if model is None:
+        model = load_model(args)
+    dev = _device_of(model)
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+    for data, lbl, folder_name in samples:
+        data = data.to(dev)
+        lbl = lbl.to(dev)
+        base_folder = args.exp_folder + "%s/" % folder_name
+        mode_folder = base_folder + "%s_all/" % args.mode
+        io = None
+        if rank == 0:
+            mkdir(mode_folder)
+            io = IOStream(mode_folder + "log.txt")
+            io.cprint(str(args))
+        norm_factor = np.load(base_folder + "norm_factor.npy")
+        region_id = np.load(base_folder + "region_id.npy")
+        load_order_list = np.load(base_folder + "all_orders.npy")
+        if io:
+            io.cprint("norm factor: %f" % norm_factor)
+        t_start = time.time()
+        orig_region_shap_value, _ = shap_sampling_all_regions_batch(model, data, lbl, region_id, load_order_list, args)
+        if io:
+            io.cprint("origin region shapley: %s" % str(orig_region_shap_value))
+            np.save(mode_folder + "orig_shapley_value.npy", orig_region_shap_value)
+
+        all_transform_params = get_transform_params_fn(args, data.device)
+        n_pose = all_transform_params.size()[0]
+        rows = args.num_samples * (args.num_regions + 1)
+        shap = torch.zeros((n_pose, args.num_regions), dtype=torch.float64, device=dev)
+        all_logits = torch.zeros((n_pose, rows, model.output_channels), dtype=torch.float32, device=dev)
+        for i in range(rank, n_pose, world):
+            transform_param = all_transform_params[i]
+            data_disturb = disturb_fn(data, transform_param)
+            region_shap_value, logits_this_pose = shap_sampling_all_regions_batch(model, data_disturb, lbl, region_id,
+                                                                                  load_order_list, args)
+            shap[i] = torch.from_numpy(region_shap_value).to(dev)
+            all_logits[i] = logits_this_pose
+            if io and world == 1:
+                print_info_fn(io, transform_param, region_shap_value, i)
+        if world > 1:
+            dist.all_reduce(shap)
+            dist.all_reduce(all_logits)
+        if rank == 0:
+            region_shapley_list = shap.cpu().numpy()
+            if world > 1:
+                for i in range(n_pose):
+                    print_info_fn(io, all_transform_params[i], region_shapley_list[i], i)
+            np.save(mode_folder + "region_shapley_value.npy", region_shapley_list)
+            torch.save(all_logits.cpu(), mode_folder + "all_logits.pt")
+            save_info_fn(all_transform_params, mode_folder)
+            io.cprint("time: %f" % (time.time() - t_start))
+            io.close()

@@ -34,6 +34,21 @@ def mkdir(path):
     os.makedirs(path, exist_ok=True)
 
 
+class IOStream():
+    """Log file + stdout, tools/final_util.py:90-100 of the reference."""
+
+    def __init__(self, path):
+        self.f = open(path, 'a')
+
+    def cprint(self, text):
+        print(text)
+        self.f.write(text + '\n')
+        self.f.flush()
+
+    def close(self):
+        self.f.close()
+
+
 def set_random(seed):
     """Seeds python hashing, numpy's legacy stream and torch exactly like the reference, so that
     replaying the same call sequence afterwards reproduces its permutations / pairs / contexts."""

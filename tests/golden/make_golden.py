@@ -195,7 +195,7 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n == "dgcnn_more":
+        elif n in ("dgcnn_more", "poses"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -217,3 +217,36 @@ def dgcnn_more():
 
 if __name__ == "__main__" and "dgcnn_more" in sys.argv[1:]:
     dgcnn_more()
+
+
+def poses():
+    """poses.npz: the pose grids and one disturbed cloud per mode from the reference's final_{trans,rotate,scale}_
+    center_enum_all.py (generate_trans_vector / generate_rotate_angle / generate_scale, translate_pc / rotate_xyz /
+    scale_pc), and the region Shapley values of three scale poses through the reference's own sampler (PointNet)."""
+    import final_trans_center_enum_all as ref_t
+    import final_rotate_center_enum_all as ref_r
+    import final_scale_center_enum_all as ref_s
+    a = types.SimpleNamespace(trans_dist_threshold=0.5, num_grid_enum_trans=6, angle_threshold=np.pi / 4,
+                              num_grid_enum_rotate=6, scale_lower=0.5, scale_upper=2.0, num_grid_enum_scale=30)
+    cpu = torch.device("cpu")
+    tv, ra, sc = ref_t.generate_trans_vector(a, cpu), ref_r.generate_rotate_angle(a, cpu), ref_s.generate_scale(a, cpu)
+    data, fps_idx, region_id = base_inputs(1024)
+    model, margs = load_ref_model("pointnet")
+    orders = synthetic.make_orders(8, R)
+    args = types.SimpleNamespace(num_points=1024, num_regions=R, shapley_batch_size=2, num_samples=4,
+                                 softmax_type="modified", model="pointnet", device=cpu)
+    a3 = types.SimpleNamespace(scale_lower=0.5, scale_upper=2.0, num_grid_enum_scale=3)
+    phis = []
+    with torch.no_grad():
+        for s in ref_s.generate_scale(a3, cpu):
+            phi, _ = ref_common.shap_sampling_all_regions_batch(model, ref_s.scale_pc(data, s), torch.tensor([LBL]),
+                                                                region_id, orders, args)
+            phis.append(phi)
+    np.savez_compressed(os.path.join(HERE, "poses.npz"), trans_vector=tv.numpy(), rotate_angle=ra.numpy(), scale=sc.numpy(),
+                        translated_7=ref_t.translate_pc(data, tv[7]).numpy(), rotated_11=ref_r.rotate_xyz(data, ra[11]).numpy(),
+                        scaled_3=ref_s.scale_pc(data, sc[3]).numpy(), scale3_pointnet_phi=np.stack(phis))
+    print("poses.npz written")
+
+
+if __name__ == "__main__" and "poses" in sys.argv[1:]:
+    poses()
