@@ -195,7 +195,7 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n in ("dgcnn_more", "poses"):
+        elif n in ("dgcnn_more", "poses", "gen_pair"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -250,3 +250,24 @@ def poses():
 
 if __name__ == "__main__" and "poses" in sys.argv[1:]:
     poses()
+
+
+def gen_pair():
+    """gen_pair.npz: gen_pair_random + gen_context of the reference's final_gen_pair.py after set_random(1)."""
+    import tempfile
+    import final_gen_pair as ref_gp
+    from tools.final_util import set_random as ref_set_random
+    a = types.SimpleNamespace(num_regions=R, num_pairs_random=6, ratio=[0.0, 0.04, 0.1, 0.5, 0.94, 1.0], num_save_context_max=100)
+    ref_set_random(1)
+    pairs = ref_gp.gen_pair_random(a)
+    d = tempfile.mkdtemp() + "/"
+    ref_gp.gen_context(pairs, d, a)
+    out = {"pairs": pairs}
+    for r in a.ratio:
+        out["ctx%d" % int(r * 100)] = np.load(d + "ratio%d_context_list.npy" % int(r * 100))
+    np.savez_compressed(os.path.join(HERE, "gen_pair.npz"), **out)
+    print("gen_pair.npz written", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__" and "gen_pair" in sys.argv[1:]:
+    gen_pair()
