@@ -195,7 +195,7 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n in ("dgcnn_more", "poses", "gen_pair"):
+        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -271,3 +271,30 @@ def gen_pair():
 
 if __name__ == "__main__" and "gen_pair" in sys.argv[1:]:
     gen_pair()
+
+
+def shap_run():
+    """shap_run.npz: the reference's final_shapley_value.shap_sampling (PointNet, CPU, 100 saved permutations) on
+    the synthetic cloud: region_sv_all, the count-100 checkpoints and norm_factor."""
+    import tempfile
+    from tools.final_util import set_random as ref_set_random
+    data, fps_idx, region_id = base_inputs(1024)
+    model, margs = load_ref_model("pointnet")
+    d = tempfile.mkdtemp() + "/"
+    os.chdir(d)
+    np.save("fps_shapenet_1024_32_index_final30.npy", np.asarray(fps_idx).reshape(1, -1))
+    a = types.SimpleNamespace(num_points=1024, num_regions=R, num_samples_save=100, softmax_type="modified", model="pointnet",
+                              dataset="shapenet", device=torch.device("cpu"), exp_folder=d + "exp/")
+    ref_set_random(1)
+    ref_sv.shap_sampling(model, [(data, torch.tensor([LBL]))], a, ["cloud0"])
+    out = d + "exp/cloud0/"
+    np.savez_compressed(os.path.join(HERE, "shap_run.npz"), region_sv_all=np.load(out + "region_sv_all.npy"),
+                        shapley_100=np.load(out + "shapley/0_100.npy"), region_shapley_100=np.load(out + "region_shapley/0_100.npy"),
+                        norm_factor=np.load(out + "norm_factor.npy"), all_orders=np.load(out + "all_orders.npy"),
+                        region_id=np.load(out + "region_id.npy"))
+    os.chdir(REF)
+    print("shap_run.npz written")
+
+
+if __name__ == "__main__" and "shap_run" in sys.argv[1:]:
+    shap_run()
