@@ -44,3 +44,14 @@ def compute_order_interaction_logits(model, data_disturb, region_id, region_pair
                                      out=masked[:rows])
                 model.forward_point_major(masked[:rows], out=out[p, 4 * s:4 * s + rows])
     return out
+
+
+def save_logits_all_orders(model, data, region_id, save_path, args):
+    """final_point_binary_interaction_logits.py:73-81: for every ratio in args.ratio, the logits of all (pair, context,
+    4 coalitions) of the pose in `data` (normal or adversarial) -> save_path/ratio%d_all_logits.pt (P, 4*ctx, C);
+    pairs and contexts are read from save_path/../ like the reference."""
+    region_pair_list = np.load(save_path + "../region_pair_list.npy")
+    for ratio in args.ratio:
+        context_list = np.load(save_path + "../ratio%d_context_list.npy" % (int(ratio * 100)))
+        all_logits = compute_order_interaction_logits(model, data, region_id, region_pair_list, context_list, args)
+        torch.save(all_logits, save_path + "ratio%d_all_logits.pt" % (int(ratio * 100)))

@@ -66,3 +66,39 @@ def test_check_adv_success_and_pred_label(tmp_path):
     pred = gp.gen_pred_label(model, data, torch.tensor([LBL]), rot.rotate_xyz, folder, a)
     saved = np.load(folder + "pred_labels.npy")
     assert saved.tolist() == [LBL, pred] and os.path.exists(folder + "pred_labels.txt")
+
+
+@pytest.mark.gpu
+def test_interaction_files_of_one_pose(tmp_path):
+    """gen_pair_random -> gen_context -> save_logits_all_orders -> cal_interaction_all_orders: the reference's
+    on-disk chain (interaction_seed<s>/region_pair_list.npy, ratio%d_context_list.npy, <pose>/ratio%d_all_logits.pt,
+    <pose>/ratio%d_gt_interaction.npy) with the values of the direct calls."""
+    from interpret_quality_b200 import final_cal_interactions as fci
+    from interpret_quality_b200 import final_point_binary_interaction_logits as fpb
+    dev = torch.device("cuda:0")
+    geo = np.load(os.path.join(os.path.dirname(__file__), "golden", "geometry.npz"))
+    data = torch.from_numpy(synthetic.make_cloud(1024))
+    rid = geo["region_id_1024"]
+    inter = str(tmp_path) + "/interaction_seed1/"
+    os.makedirs(inter + "normal/")
+    a = types.SimpleNamespace(model="gcnn", k=20, dataset="shapenet", device=dev, num_points=1024, num_regions=R,
+                              softmax_type="modified", num_pairs_random=3, ratio=[0.0, 0.1, 1.0], num_save_context_max=10,
+                              output_type="gt")
+    final_util.set_random(1)
+    pairs = gp.gen_pair_random(a)
+    np.save(inter + "region_pair_list.npy", pairs)
+    gp.gen_context(pairs, inter, a)
+    model = final_util.build_model(a, synthetic.make_state_dict("gcnn"))
+    fpb.save_logits_all_orders(model, data, rid, inter + "normal/", a)
+    fci.cal_interaction_all_orders(torch.tensor([LBL]), inter + "normal/", a)
+    for pct, ctx in ((0, 1), (10, 10), (100, 1)):
+        lg = torch.load(inter + "normal/ratio%d_all_logits.pt" % pct)
+        it = np.load(inter + "normal/ratio%d_gt_interaction.npy" % pct)
+        assert tuple(lg.shape) == (3, 4 * ctx, 10) and lg.dtype == torch.float32
+        assert it.shape == (3, ctx) and it.dtype == np.float64
+        direct = fpb.compute_order_interaction_logits(model, data, rid, pairs, np.load(inter + "ratio%d_context_list.npy" % pct), a)
+        assert torch.equal(direct.cpu(), lg.cpu())
+        assert np.array_equal(fci.compute_order_interaction(direct, torch.tensor([LBL]), a), it)
+    # m = R-2: the context is everything but the pair, so S+{i,j} is the full cloud for every pair
+    full = torch.load(inter + "normal/ratio100_all_logits.pt")[:, 0]
+    assert torch.allclose(full[0], full[1]) and torch.allclose(full[0], full[2])
