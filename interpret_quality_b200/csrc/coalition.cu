@@ -160,6 +160,8 @@ int launch_mask_interaction(const float *data, const float *center, const int64_
 
 // ------------------------------------------------------------------ reward
 // modified: z_y - logsumexp(z_{!=y})  (= log p/(1-p));  normal: log_softmax(z)_y.
+// exp / log through the SFU (ex2.approx / lg2.approx, ~2 ulp): with libm's expf / logf the 10 exponentials per row made
+// these kernels ALU-bound at 0.15 of the copy bandwidth; the rewards move by ~1e-7 of their scale.
 __device__ __forceinline__ float reward_of_row(const float *z, int C, int lbl, int softmax_normal)
 {
     float mx = -INFINITY;
@@ -167,9 +169,9 @@ __device__ __forceinline__ float reward_of_row(const float *z, int C, int lbl, i
         if (softmax_normal || c != lbl) mx = fmaxf(mx, z[c]);
     float s = 0.0f;
     for (int c = 0; c < C; ++c)
-        if (softmax_normal || c != lbl) s += expf(z[c] - mx);
+        if (softmax_normal || c != lbl) s += __expf(z[c] - mx);
     // log_softmax subtracts the max first; logsumexp adds it back last
-    return softmax_normal ? (z[lbl] - mx) - logf(s) : z[lbl] - (logf(s) + mx);
+    return softmax_normal ? (z[lbl] - mx) - __logf(s) : z[lbl] - (__logf(s) + mx);
 }
 
 // A row of logits is 40 bytes (160 for the 4 clouds of a context): read one row per thread, a warp touches 10-40 lines per
@@ -181,9 +183,22 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ src, int64_
     const int rows = (int)min((int64_t)blockDim.x, total_rows - first_row);
     const float *base = src + first_row * row_len;
     const int n = rows * row_len, stride = row_len | 1;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int r = t / row_len, c = t - r * row_len;
-        smem[r * stride + c] = __ldg(base + t);
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {        // 16-byte loads, 4x the bytes in flight
+        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(base) + t);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            int r = (4 * t) / row_len, c = 4 * t - r * row_len;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                smem[r * stride + c] = e[j];
+                if (++c == row_len) { c = 0; ++r; }
+            }
+        }
+    } else {
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int r = t / row_len, c = t - r * row_len;
+            smem[r * stride + c] = __ldg(base + t);
+        }
     }
     __syncthreads();
 }
@@ -262,14 +277,15 @@ int launch_shapley_accumulate(const float *v, const int64_t *orders, int64_t bs,
 // ------------------------------------------------------------------ interaction score
 // out[p][k] = double((v[4k] + v[4k+3]) - v[4k+1] - v[4k+2]) with the fp32
 // operation order of final_cal_interactions.py:33.
-// 40 expf + 4 logf per context against 168 bytes: bound by the SFU / ALU work of the exact softmax, not by HBM
-// (staging the rows in shared memory like reward_kernel measured no gain).
 __global__ void interaction_reduce_kernel(const float *__restrict__ logits, int64_t total, int C, int lbl,
                                           int softmax_normal, double *__restrict__ out)
 {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    extern __shared__ float rows_s[];
+    const int64_t first = blockIdx.x * (int64_t)blockDim.x;
+    stage_rows(logits, first, total, 4 * C, rows_s);
+    const int64_t t = first + threadIdx.x;
     if (t >= total) return;
-    const float *z = logits + t * 4 * C;
+    const float *z = rows_s + threadIdx.x * ((4 * C) | 1);
     const float v0 = reward_of_row(z, C, lbl, softmax_normal);
     const float v1 = reward_of_row(z + C, C, lbl, softmax_normal);
     const float v2 = reward_of_row(z + 2 * C, C, lbl, softmax_normal);
@@ -281,11 +297,18 @@ int launch_interaction_reduce(const float *logits, int64_t P, int64_t ctx, int64
                               double *out, cudaStream_t st)
 {
     ProfileScope _ps("interaction_reduce", st);
-    IQ_CHECK(C >= 2 && lbl >= 0 && lbl < C, "interaction_reduce: label out of range");
+    IQ_CHECK(C >= 2 && C <= 256 && lbl >= 0 && lbl < C, "interaction_reduce: label out of range");
     const int64_t total = P * ctx;
     if (total == 0) return 0;
-    interaction_reduce_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(logits, total, (int)C, (int)lbl,
-                                                                             softmax_normal, out);
+    const int threads = C <= 64 ? 128 : 32;
+    const size_t smem = sizeof(float) * threads * (size_t)((4 * C) | 1);
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        IQ_CUDA(cudaFuncSetAttribute(interaction_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    interaction_reduce_kernel<<<(unsigned)ceil_div(total, threads), threads, smem, st>>>(logits, total, (int)C, (int)lbl,
+                                                                                        softmax_normal, out);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;

@@ -3,13 +3,13 @@ against the copy bandwidth of MEASURED_PEAKS.json.  Writes a markdown table (pro
 
     python scripts/bench_kernels.py [out.md]
 
-Timing: CUDA events on the launching stream, 3 warm-ups, median of 10, a 256 MiB buffer rewritten between repeats
-(L2 flush)."""
+Timing: the library's own CUDA events around each launch on the launching stream (iq_profile_enable: no host time in
+the bracket), 3 warm-ups, mean of 10, a 256 MiB buffer rewritten between repeats (L2 flush)."""
 import json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from interpret_quality_b200 import ops, synthetic
+from interpret_quality_b200 import _lib, ops, synthetic
 
 dev = "cuda:0"
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
@@ -20,14 +20,16 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def timed(fn, reps=10):
     for _ in range(3):
         fn()
-    ms = []
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
     for _ in range(reps):
         flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
-        torch.cuda.synchronize()
-        ms.append(a.elapsed_time(b))
-    return float(np.median(ms))
+        fn()
+    rep = _lib.profile_report()
+    _lib.profile_enable(False)
+    assert len(rep) == 1, rep
+    (total_ms, n), = rep.values()
+    return total_ms / n
 
 
 rows = []
