@@ -42,7 +42,10 @@ __device__ __forceinline__ float sqn3(float x, float y, float z)
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
 }
 
-// inverse KDE density of every point of a cloud; one thread per point, cloud staged in shared memory
+// inverse KDE density of every point of a cloud (compute_density, models/pointconv.py:199-209, then 1/density);
+// one thread per point, cloud staged in shared memory.  The density only feeds DensityNet (a float path, no discrete
+// decision), so the N x N Gaussian runs on the SFU: exp(-d / 2bw^2) = ex2(d * c), one multiply by 1/(2.5 bw N) at the
+// end (the exact div.rn / expf form measured 4x slower: 15.5 ms per 3300 clouds).
 __global__ void __launch_bounds__(256)
 density_kernel(const float *__restrict__ xyz, int N, float two_bw2, float norm, float *__restrict__ inv_density)
 {
@@ -57,13 +60,17 @@ density_kernel(const float *__restrict__ xyz, int N, float two_bw2, float norm, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const float4 q = pts[i];
-    float acc = 0.0f;
-    for (int j = 0; j < N; ++j) {
-        const float4 c = pts[j];
-        const float d = sqdist3_exact(q.x, q.y, q.z, q.w, c.x, c.y, c.z, c.w);
-        acc += __fdiv_rn(expf(__fdiv_rn(-d, two_bw2)), norm);
+    const float c = -1.4426950408889634f / two_bw2;               // log2(e) / (2 bw^2), negated
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int j = 0; j < N; j += 2) {
+        const float4 c0 = pts[j], c1 = pts[min(j + 1, N - 1)];
+        const float d0 = sqdist3_exact(q.x, q.y, q.z, q.w, c0.x, c0.y, c0.z, c0.w);
+        const float d1 = sqdist3_exact(q.x, q.y, q.z, q.w, c1.x, c1.y, c1.z, c1.w);
+        acc0 += exp2f(d0 * c);
+        if (j + 1 < N) acc1 += exp2f(d1 * c);
     }
-    inv_density[(int64_t)b * N + i] = __fdiv_rn(1.0f, __fdiv_rn(acc, (float)N));
+    const float density = (acc0 + acc1) / (norm * (float)N);
+    inv_density[(int64_t)b * N + i] = 1.0f / density;
 }
 
 // per-cloud mean of the points (sample_and_group_all, models/pointconv.py:160)
@@ -146,41 +153,75 @@ small_nets_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
     }
 }
 
-// agg[cen][c*16 + w] = sum_j H3[cen*K + j][c] * Wd[cen*K + j][w];  one CTA per centroid, Wd tile in shared memory
-__global__ void __launch_bounds__(256)
-aggregate_kernel(const float *__restrict__ H3, const float *__restrict__ Wd, int K, int C, float *__restrict__ agg,
-                 float *__restrict__ agg_hi, float *__restrict__ agg_lo, int64_t ld)
+// agg[cen][c*16 + w] = sum_j H3[cen*K + j][c] * Wd[cen*K + j][w]  (models/pointconv.py:378-380, the per-centroid
+// (C x K)(K x 16) product).  One warp per (centroid, block of 128 channels): a lane owns 4 channels x 16 weights = 64
+// accumulators, reads its 4 channels of a neighbour row as one float4 (512 B per warp, coalesced) and the 16 weights of
+// that neighbour as four broadcast float4 loads, so the loop is 64 FMAs per 5 loads; the result leaves as 256
+// contiguous bytes per lane.  (The first version used one thread per channel with 16 scalar shared-memory reads per
+// FMA group and ran at 0.15 of the FMA peak.)
+__global__ void __launch_bounds__(256, 2)
+aggregate_kernel(const float *__restrict__ H3, const float *__restrict__ Wd, int64_t cents, int K, int C,
+                 float *__restrict__ agg, float *__restrict__ agg_hi, float *__restrict__ agg_lo, int64_t ld)
 {
-    extern __shared__ float wd[];                                  // K x 16
-    const int64_t cen = blockIdx.x;
-    for (int t = threadIdx.x; t < K * 16; t += blockDim.x) wd[t] = Wd[cen * K * 16 + t];
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc[16];
+    extern __shared__ float4 wd_s[];                               // per warp: K x 16 weights of its centroid
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int blocks_per_cen = C >> 7;
+    const int64_t unit = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (unit >= cents * blocks_per_cen) return;
+    const int64_t cen = unit / blocks_per_cen;
+    const int cb = (int)(unit - cen * blocks_per_cen);
+    const float4 *h = reinterpret_cast<const float4 *>(H3 + cen * K * (int64_t)C + cb * 128) + lane;
+    float4 *w = wd_s + wib * (K * 4);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(Wd + cen * K * 16);
+        for (int t = lane; t < K * 4; t += 32) w[t] = __ldg(src + t);
+        __syncwarp();
+    }
+    float acc[4][16];
 #pragma unroll
-        for (int w = 0; w < 16; ++w) acc[w] = 0.0f;
-        for (int j = 0; j < K; ++j) {
-            const float h = H3[(cen * K + j) * C + c];
+    for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int w = 0; w < 16; ++w) acc[w] = fmaf(h, wd[j * 16 + w], acc[w]);
-        }
-        const int64_t o = cen * ld + (int64_t)c * 16;
+        for (int q = 0; q < 16; ++q) acc[e][q] = 0.0f;
+    const int64_t hs = C >> 2;
+    for (int j0 = 0; j0 < K; j0 += 4) {                              // K is a multiple of 4; four rows in flight
+        float4 hv[4];
 #pragma unroll
-        for (int w = 0; w < 16; w += 4) {
-            if (agg) *reinterpret_cast<float4 *>(agg + o + w) = make_float4(acc[w], acc[w + 1], acc[w + 2], acc[w + 3]);
-            if (agg_hi) {
-                float h4[4], l4[4];
+        for (int u = 0; u < 4; ++u) hv[u] = __ldg(h + (int64_t)(j0 + u) * hs);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    h4[q] = __uint_as_float((__float_as_uint(acc[w + q]) + 0x1000u) & 0xffffe000u);
-                    const float d = acc[w + q] - h4[q];
-                    l4[q] = __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xffffe000u);
+        for (int u = 0; u < 4; ++u) {
+            const float he[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 wv = w[(j0 + u) * 4 + q];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[e][4 * q] = fmaf(he[e], wv.x, acc[e][4 * q]);
+                    acc[e][4 * q + 1] = fmaf(he[e], wv.y, acc[e][4 * q + 1]);
+                    acc[e][4 * q + 2] = fmaf(he[e], wv.z, acc[e][4 * q + 2]);
+                    acc[e][4 * q + 3] = fmaf(he[e], wv.w, acc[e][4 * q + 3]);
                 }
-                *reinterpret_cast<float4 *>(agg_hi + o + w) = make_float4(h4[0], h4[1], h4[2], h4[3]);
-                *reinterpret_cast<float4 *>(agg_lo + o + w) = make_float4(l4[0], l4[1], l4[2], l4[3]);
             }
         }
     }
+    const int64_t o = cen * ld + (int64_t)(cb * 128 + lane * 4) * 16;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+            const float *a = &acc[e][q];
+            if (agg) *reinterpret_cast<float4 *>(agg + o + e * 16 + q) = make_float4(a[0], a[1], a[2], a[3]);
+            if (agg_hi) {
+                float h4[4], l4[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    h4[t] = __uint_as_float((__float_as_uint(a[t]) + 0x1000u) & 0xffffe000u);
+                    const float d = a[t] - h4[t];
+                    l4[t] = __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xffffe000u);
+                }
+                *reinterpret_cast<float4 *>(agg_hi + o + e * 16 + q) = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                *reinterpret_cast<float4 *>(agg_lo + o + e * 16 + q) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+            }
+        }
 }
 
 struct SaLayer {
@@ -292,9 +333,18 @@ protected:
         {
             ProfileScope _ps("aggregate", st);
             const bool to_lin = agg_out == nullptr;                   // sa1 / sa2: feed the Linear right away
-            aggregate_kernel<<<(unsigned)cents, 256, sizeof(float) * 16 * (size_t)K, st>>>(
-                s.h3, s.wd, K, L.c3, (to_lin && tc) ? nullptr : (to_lin ? s.agghi : agg_out), (to_lin && tc) ? s.agghi : nullptr,
-                (to_lin && tc) ? s.agglo : nullptr, 16 * (int64_t)L.c3);
+            IQ_CHECK(L.c3 % 128 == 0, "pointconv: aggregate needs a channel count that is a multiple of 128");
+            const int64_t warps = cents * (L.c3 / 128);
+            IQ_CHECK(K % 4 == 0 && K <= 512, "pointconv: aggregate needs a neighbour count that is a multiple of 4");
+            const size_t agg_smem = sizeof(float) * 16 * (size_t)K * 8;
+            static size_t agg_smem_set = 48 * 1024;
+            if (agg_smem > agg_smem_set) {
+                IQ_CUDA(cudaFuncSetAttribute(aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem));
+                agg_smem_set = agg_smem;
+            }
+            aggregate_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, agg_smem, st>>>(
+                s.h3, s.wd, cents, K, L.c3, (to_lin && tc) ? nullptr : (to_lin ? s.agghi : agg_out),
+                (to_lin && tc) ? s.agghi : nullptr, (to_lin && tc) ? s.agglo : nullptr, 16 * (int64_t)L.c3);
             IQ_COUNT_LAUNCH();
             IQ_LAUNCH_CHECK();
         }
