@@ -174,6 +174,11 @@ class ClockSampler:
 TF32_TFLOPS_MEASURED = 1100.0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's ncu --set full capture of one 148-cloud chunk
+# (profiles/r1_v4_full_summary.md; cold-cache kernel replay).  Only quoted for the default workload it was captured on.
+NCU_TRAFFIC_BYTES = {"tc_conv5_pool": 295.3e6, "tc_edge_pq": 156.7e6, "tc_gram_knn_c64": 89.7e6, "knn_xyz": 1.9e6}
+
+
 def kernel_work(a):
     """Algorithmic work per forward (one masked cloud) of the kernel families, for the roofline leg (DESIGN.md
     section 4).  "tensor": (logical FLOPs = 2*MAC of the fp32 product the kernel evaluates, tcgen05 MMAs executed per
@@ -355,8 +360,9 @@ def run_b200(a):
                 ach, peak, unit = per_launch / dur / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
             else:
                 ach, peak, unit = per_launch / dur / 1e9, pk["hbm_gbs"], "GB/s"
+            default_workload = a.model == "dgcnn" and a.points == 1024 and a.perms == 100 and not a.chunk
             k = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                 "traffic": None, "avg_launch_ms": dur * 1e3, "launches_per_step": n, "share_of_step": ms / tot,
+                 "traffic": NCU_TRAFFIC_BYTES.get(name) if default_workload else None, "avg_launch_ms": dur * 1e3, "launches_per_step": n, "share_of_step": ms / tot,
                  "algorithmic_per_launch": per_launch, "peak_source": pk["source"]}
             if bound == "tensor":
                 # the kernels compute fp32 products as `mult` tf32 MMAs each: the executed rate is what the tensor pipe
