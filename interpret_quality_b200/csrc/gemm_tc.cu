@@ -36,32 +36,44 @@ using namespace tc;
 namespace {
 
 constexpr int TC_THREADS = 192;
+constexpr int GA_THREADS = 256;          // gathered-A variant: two groups of four gather warps, alternating ring stages
 
+// Kernel parameters.  Together with the seven 128-byte tensor maps they must stay within 1024 bytes: one 64-byte field more
+// and every variant of the kernel ran 25-50 % slower on B200 (measured by padding this struct: PointNet conv+pool 10.5 ->
+// 15.6 ms), so the POOL-only and the gather-only fields share storage and the STORE outputs are flags (they leave via TMA).
 struct TcParams {
-    int K;                       // multiple of 32
-    int mode;                    // 0 = STORE, 1 = POOL
+    int K;                       // multiple of 4 (TMA zero-fills up to the next multiple of 32)
     // STORE: units = (M/128) * (Ncols/BN), one accumulator tile each
     int n_tiles;                 // Ncols / BN
     int rows_per_batch;          // > 0: B rows live in the same batch as the A rows (Gram), else B is shared
-    // POOL: columns are grouped in runs of `points` consecutive B rows (points of a cloud / neighbours of a centroid).
-    //   points >= BN: units = groups * m_tiles, tiles_per_unit = points / BN (running reduction across tiles)
-    //   points <  BN: units = column tiles * m_tiles, BN / points groups reduced inside one tile
-    int m_tiles;                 // ceil(Cout / 128)
-    int points;                  // columns per group
     int num_units, tiles_per_unit;
-    float alpha;
-    const float *bias;           // STORE: per column (index b_row0 + c), POOL: per row (channel)
     int act;
-    float *C;                    // STORE outputs: fp32 and / or its tf32 hi/lo split (same leading dimension)
-    float *C_hi, *C_lo;
-    int64_t ldc;
-    float *out_max;              // POOL outputs, (clouds, ld_out)
-    float *out_mean;
-    int64_t *out_arg;            // (clouds, Cout)
-    int64_t ld_out;
-    int cout;
+    int out_c, out_hilo;         // STORE outputs present: fp32 and / or its tf32 hi/lo split
+    float alpha;
     int dbg;                     // IQ_TC_DBG (scripts/tc_probe.py): 1 = STORE epilogue skips its math and stores
+    const float *bias;           // STORE: per column (index b_row0 + c), POOL: per row (channel)
+    union {
+        // POOL: columns are grouped in runs of `points` consecutive B rows (points of a cloud / neighbours of a centroid).
+        //   points >= BN: units = groups * m_tiles, tiles_per_unit = points / BN (running reduction across tiles)
+        //   points <  BN: units = column tiles * m_tiles, BN / points groups reduced inside one tile
+        struct {
+            float *out_max, *out_mean;   // (clouds, ld_out)
+            int64_t *out_arg;            // (clouds, Cout)
+            int64_t ld_out;
+            int cout;
+            int m_tiles;                 // ceil(Cout / 128)
+            int points;                  // columns per group
+        };
+        // gathered-A STORE: A[row][c] = act(U[cloud*nsrc + idx[row]][c] - V[row / gK][c] + gbias[c]), cloud = row / (gK * gS)
+        struct {
+            const float *gU, *gV, *gbias;
+            const int32_t *gidx;
+            int64_t gldu, gldv;
+            int gK, gS, gnsrc, gact;
+        };
+    };
 };
+static_assert(sizeof(TcParams) + 7 * 128 <= 1024, "kernel parameters must stay within 1 KB (see above)");
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -98,14 +110,26 @@ __device__ __forceinline__ void store_box(const CUtensorMap *map, const float (&
     ++nbox;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// GA ("gathered A", STORE mode): the first grouped-MLP layer of PointNet++ / PointConv, relu(U[idx] - V + b), used to be
+// written to HBM as a tf32 hi/lo pair by one kernel and read back by this one -- 45 % of the HBM traffic of a grouped
+// MLP chain that is HBM bound.  Eight extra warps (thread = row of the tile, two groups on alternate stages) now gather U, apply the layer and write the
+// hi and lo operand tiles straight into the 128B-swizzled ring slots; TMA only brings the weights.
+// The epilogue variant is a template parameter (VAR_*): with run-time mode switches inside one kernel the compiler's
+// unswitching / unrolling choices for one variant moved whenever another was touched (POOL 85 -> 130 ms on PointNet++
+// after an unrelated edit).
+enum : int { VAR_STORE = 0, VAR_POOL_RUN = 1, VAR_POOL_TILE = 2, VAR_STORE_GATHER = 3 };
+template <int BN, int STAGES, int VAR>
+__global__ void __launch_bounds__(TC_THREADS + (VAR == VAR_STORE_GATHER ? GA_THREADS : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_chi,
                const __grid_constant__ CUtensorMap map_clo, const TcParams p)
 {
     using S = TcSmem<BN, STAGES>;
+    constexpr bool GA = VAR == VAR_STORE_GATHER;
+    constexpr bool STORE = VAR == VAR_STORE || VAR == VAR_STORE_GATHER;
+    constexpr bool POOL_RUN = VAR == VAR_POOL_RUN;                          // groups of >= BN columns: running reduction
+    constexpr uint32_t FULL_ARRIVALS = GA ? 5 : 1;                          // TMA producer (+ the four gather warps)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *out_stage = smem + STAGES * S::STAGE_BYTES;                    // 1024-byte aligned (stages are multiples of 1 KB)
@@ -120,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_ahi); prefetch_tmap(&map_alo); prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], FULL_ARRIVALS); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         fence_barrier_init();
     }
@@ -134,14 +158,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     const uint32_t tmem_base = *tmem_ptr;
 
     auto tile_rows = [&](int unit, int j, int &a_row0, int &b_row0) {
-        if (p.mode == 0) {
+        if (STORE) {
             const int mt = unit / p.n_tiles, nt = unit - mt * p.n_tiles;
             a_row0 = mt * TBM;
             b_row0 = nt * BN + (p.rows_per_batch > 0 ? (a_row0 / p.rows_per_batch) * p.rows_per_batch : 0);
         } else {
             const int grp = unit / p.m_tiles, mt = unit - grp * p.m_tiles;
             a_row0 = mt * TBM;
-            b_row0 = p.points >= BN ? grp * p.points + j * BN : grp * BN;
+            b_row0 = POOL_RUN ? grp * p.points + j * BN : grp * BN;
         }
     };
 
@@ -158,9 +182,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *st = smem + stage * S::STAGE_BYTES;
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                        tma_load_2d(st, &map_ahi, &full_bar[stage], kb * TBK, a_row0);
-                        tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * TBK, a_row0);
+                        mbar_arrive_expect_tx(&full_bar[stage], GA ? 2 * S::B_BYTES : S::STAGE_BYTES);
+                        if (!GA) {
+                            tma_load_2d(st, &map_ahi, &full_bar[stage], kb * TBK, a_row0);
+                            tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * TBK, a_row0);
+                        }
                         tma_load_2d(st + 2 * S::A_BYTES, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
                         tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_blo, &full_bar[stage], kb * TBK, b_row0);
                     }
@@ -203,6 +229,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+    } else if (GA && warp >= 6) {
+        // ---- gather warps: thread = row of the tile, one 32-channel block per ring stage; the two groups of four warps
+        // take alternate stages so that two stages' worth of gathers are in flight
+        const int r = ((int)threadIdx.x - 192) & 127, grp = ((int)threadIdx.x - 192) >> 7;
+        const int sw = r & 7;
+        int stage = 0, turn = 0;
+        uint32_t phase = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+            int a_row0, b_row0;
+            tile_rows(unit, 0, a_row0, b_row0);
+            const int64_t row = (int64_t)a_row0 + r;
+            const int64_t cen = row / p.gK, cloud = cen / p.gS;
+            const float *u = p.gU + (cloud * p.gnsrc + __ldg(p.gidx + row)) * p.gldu;
+            const float *v = p.gV + cen * p.gldv;
+            for (int kb = 0; kb < kblocks; ++kb, turn ^= 1) {
+                if (turn != grp) {                                    // the other group's stage
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+                }
+                float4 uu[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    uu[q] = kb * TBK + 4 * q < p.K ? __ldg(reinterpret_cast<const float4 *>(u + kb * TBK) + q)
+                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const uint32_t hi_row = smem_u32(smem + stage * S::STAGE_BYTES) + (uint32_t)r * 128u;
+                const uint32_t lo_row = hi_row + S::A_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float h[4] = {0.0f, 0.0f, 0.0f, 0.0f}, l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (kb * TBK + 4 * q < p.K) {
+                        const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + kb * TBK) + q);
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.gbias + kb * TBK) + q);
+                        const float x[4] = {apply_act((uu[q].x - vv.x) + bb.x, p.gact), apply_act((uu[q].y - vv.y) + bb.y, p.gact),
+                                            apply_act((uu[q].z - vv.z) + bb.z, p.gact), apply_act((uu[q].w - vv.w) + bb.w, p.gact)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { h[e] = tf32_round(x[e]); l[e] = tf32_round(x[e] - h[e]); }
+                    }
+                    const uint32_t off = (uint32_t)((q ^ sw) << 4);
+                    sts128(hi_row + off, h[0], h[1], h[2], h[3]);
+                    sts128(lo_row + off, l[0], l[1], l[2], l[3]);
+                }
+                fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA's async reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
     } else {
         const int quad = warp & 3;                                       // TMEM lane quadrant this warp may read
         const int row_in_tile = quad * 32 + lane;
@@ -217,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                if (p.mode == 0) {
+                if (STORE) {
                     // The accumulator arrives one ROW per thread; stored that way a warp touches 32 rows per instruction
                     // and the epilogue, not the MMAs, paced the kernel (measured 76 us vs 25 us without it).  Each warp
                     // now writes its 32 x 32 block into a 128B-swizzled shared-memory box (conflict-free 16-byte
@@ -236,8 +310,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = apply_act(fmaf(p.alpha, v[i], bv[i]), p.act);
                         const int col = nt * BN + c0;
-                        if (p.C) store_box(&map_c, v, box0, nbox, lane, sw, col, out_row);
-                        if (p.C_hi) {
+                        if (p.out_c) store_box(&map_c, v, box0, nbox, lane, sw, col, out_row);
+                        if (p.out_hilo) {
                             float h[32];
 #pragma unroll
                             for (int i = 0; i < 32; ++i) { h[i] = tf32_round(v[i]); v[i] = tf32_round(v[i] - h[i]); }
@@ -253,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     for (int c0 = 0; c0 < BN; c0 += 32) {
                         float v[32];
                         tmem_ld32(taddr + c0, v);
-                        if (p.points >= BN) {
+                        if (POOL_RUN) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const float y = apply_act(fmaf(p.alpha, v[i], b), p.act);
@@ -279,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (p.mode == 1 && p.points >= BN) {
+            if (POOL_RUN) {
                 const int grp = unit / p.m_tiles, mt = unit - grp * p.m_tiles;
                 const int ch = mt * TBM + row_in_tile;
                 if (ch < p.cout) {
@@ -291,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         }
     }
 
-    if (warp >= 2 && lane == 0) bulk_wait_all();                     // every TMA store of this warp has landed
+    if (warp >= 2 && warp < 6 && lane == 0) bulk_wait_all();                     // every TMA store of this warp has landed
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -350,15 +424,20 @@ bool tc_gemm_supported(const TcGemm &g)
     return 128 % g.points == 0 && ((int64_t)g.clouds * g.points) % 128 == 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int VAR>
 static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_t b_rows, cudaStream_t st)
 {
     using S = TcSmem<BN, STAGES>;
     CUtensorMap mahi, malo, mbhi, mblo;
-    if (int rc = make_map(&mahi, g.A_hi, a_rows, g.K, g.lda, TBM)) return rc;
-    if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
     if (int rc = make_map(&mbhi, g.B_hi, b_rows, g.K, g.ldb, BN)) return rc;
     if (int rc = make_map(&mblo, g.B_lo, b_rows, g.K, g.ldb, BN)) return rc;
+    constexpr bool GA = VAR == VAR_STORE_GATHER;
+    if (GA) {
+        mahi = mbhi; malo = mblo;                               // unused: the A tiles are produced in the kernel
+    } else {
+        if (int rc = make_map(&mahi, g.A_hi, a_rows, g.K, g.lda, TBM)) return rc;
+        if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
+    }
     // STORE outputs leave through TMA: 32 x 32 boxes (128 bytes wide) over each fp32 output matrix
     CUtensorMap mc = mahi, mchi = mahi, mclo = mahi;
     if (g.mode == 0) {
@@ -370,11 +449,11 @@ static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_
     }
     static bool attr_set = false;
     if (!attr_set) {
-        IQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        IQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
     const int grid = std::min(p.num_units, sm_count());
-    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(mahi, malo, mbhi, mblo, mc, mchi, mclo, p);
+    gemm_tc_kernel<BN, STAGES, VAR><<<grid, TC_THREADS + (GA ? GA_THREADS : 0), S::TOTAL, st>>>(mahi, malo, mbhi, mblo, mc, mchi, mclo, p);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -385,15 +464,14 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
     ProfileScope _ps(g.tag, st);
     IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape");
     TcParams p = {};
-    p.K = g.K; p.mode = g.mode; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
+    p.K = g.K; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
     const char *dbg = getenv("IQ_TC_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
     int64_t a_rows, b_rows;
     int bn;
     if (g.mode == 0) {
         bn = pick_bn(g.N);
-        p.n_tiles = g.N / bn; p.rows_per_batch = g.rows_per_batch; p.C = g.C; p.C_hi = g.C_hi; p.C_lo = g.C_lo;
-        p.ldc = g.ldc;
+        p.n_tiles = g.N / bn; p.rows_per_batch = g.rows_per_batch; p.out_c = g.C != nullptr; p.out_hilo = g.C_hi != nullptr;
         p.num_units = (g.M / TBM) * p.n_tiles; p.tiles_per_unit = 1;
         a_rows = g.M;
         b_rows = g.rows_per_batch > 0 ? g.M : g.N;
@@ -410,11 +488,26 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
         IQ_CHECK(g.points >= bn || (!g.out_mean && !g.out_arg), "gemm_tc: mean / argmax need groups of >= 128 columns");
     }
     if (p.num_units == 0) return 0;
+    if (g.gather.U) {
+        IQ_CHECK(g.mode == 0 && g.N == bn, "gemm_tc: the gathered-A variant takes one column tile (N in {32, 64, 96, 128})");
+        IQ_CHECK(g.gather.ldu % 4 == 0 && g.gather.ldv % 4 == 0 && g.K % 4 == 0, "gemm_tc: gathered-A widths must be multiples of 4");
+        p.gU = g.gather.U; p.gV = g.gather.V; p.gbias = g.gather.bias; p.gidx = g.gather.idx; p.gldu = g.gather.ldu;
+        p.gldv = g.gather.ldv; p.gK = g.gather.K; p.gS = g.gather.S; p.gnsrc = g.gather.nsrc; p.gact = g.gather.act;
+        switch (bn) {
+        case 128: return launch_tc_variant<128, 3, VAR_STORE_GATHER>(g, p, a_rows, b_rows, st);
+        case 96: return launch_tc_variant<96, 3, VAR_STORE_GATHER>(g, p, a_rows, b_rows, st);
+        case 64: return launch_tc_variant<64, 4, VAR_STORE_GATHER>(g, p, a_rows, b_rows, st);
+        default: return launch_tc_variant<32, 4, VAR_STORE_GATHER>(g, p, a_rows, b_rows, st);
+        }
+    }
+    if (g.mode == 1)
+        return g.points >= bn ? launch_tc_variant<128, 3, VAR_POOL_RUN>(g, p, a_rows, b_rows, st)
+                              : launch_tc_variant<128, 3, VAR_POOL_TILE>(g, p, a_rows, b_rows, st);
     switch (bn) {
-    case 128: return launch_tc_variant<128, 3>(g, p, a_rows, b_rows, st);
-    case 96: return launch_tc_variant<96, 3>(g, p, a_rows, b_rows, st);
-    case 64: return launch_tc_variant<64, 4>(g, p, a_rows, b_rows, st);
-    default: return launch_tc_variant<32, 4>(g, p, a_rows, b_rows, st);
+    case 128: return launch_tc_variant<128, 3, VAR_STORE>(g, p, a_rows, b_rows, st);
+    case 96: return launch_tc_variant<96, 3, VAR_STORE>(g, p, a_rows, b_rows, st);
+    case 64: return launch_tc_variant<64, 4, VAR_STORE>(g, p, a_rows, b_rows, st);
+    default: return launch_tc_variant<32, 4, VAR_STORE>(g, p, a_rows, b_rows, st);
     }
 }
 

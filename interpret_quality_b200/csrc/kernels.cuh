@@ -74,6 +74,15 @@ struct TcGemm {
     const float *bias = nullptr;  // STORE: per output column; POOL: per output channel
     int act = ACT_NONE;
     const char *tag = "gemm_tc";
+    // STORE only, optional: produce the A rows on the fly from a grouping instead of reading A_hi / A_lo,
+    //   A[row][c] = act(U[cloud*nsrc + idx[row]][c] - V[row / K][c] + bias[c]),  cloud = row / (K * S)
+    // (the first layer of a grouped MLP: launch_group_sub_act fused into its consumer); needs N <= 128
+    struct Gather {
+        const float *U = nullptr, *V = nullptr, *bias = nullptr;
+        const int32_t *idx = nullptr;
+        int64_t ldu = 0, ldv = 0;
+        int K = 0, S = 0, nsrc = 0, act = ACT_NONE;
+    } gather;
 };
 bool tc_gemm_supported(const TcGemm &g);
 int launch_gemm_tc(const TcGemm &g, cudaStream_t st);

@@ -303,11 +303,17 @@ protected:
         if (int rc = sgemm(new_xyz, 3, L.w1x, 3, nullptr, s.V, L.c1, cents, L.c1, 3, ACT_NONE, "sgemm_sa_centroid", st))
             return rc;
         const bool tc = engine == 1;
-        if (int rc = launch_group_sub_act(s.U, L.c1, s.V, L.c1, L.b1, s.idx, Bc, S, K, Nsrc, L.c1, ACT_RELU,
-                                          tc ? nullptr : s.h1hi, tc ? s.h1hi : nullptr, tc ? s.h1lo : nullptr, L.c1, st))
-            return rc;
+        const bool fuse12 = tc && L.c2 <= 128 && rows % 128 == 0;   // layers 1 + 2 in one kernel (gemm_tc.cu, gathered A)
+        if (!fuse12)
+            if (int rc = launch_group_sub_act(s.U, L.c1, s.V, L.c1, L.b1, s.idx, Bc, S, K, Nsrc, L.c1, ACT_RELU,
+                                              tc ? nullptr : s.h1hi, tc ? s.h1hi : nullptr, tc ? s.h1lo : nullptr, L.c1, st))
+                return rc;
         if (tc) {
             TcGemm a;
+            if (fuse12) {
+                a.gather.U = s.U; a.gather.ldu = L.c1; a.gather.V = s.V; a.gather.ldv = L.c1; a.gather.bias = L.b1;
+                a.gather.idx = s.idx; a.gather.K = K; a.gather.S = S; a.gather.nsrc = Nsrc; a.gather.act = ACT_RELU;
+            }
             a.A_hi = s.h1hi; a.A_lo = s.h1lo; a.lda = L.c1; a.B_hi = L.l2.w_hi; a.B_lo = L.l2.w_lo; a.ldb = L.c1;
             a.K = L.c1; a.M = (int)rows; a.N = L.c2; a.C_hi = s.h2hi; a.C_lo = s.h2lo; a.ldc = L.c2; a.bias = L.l2.b;
             a.act = ACT_RELU; a.tag = "tc_sa_mlp2";

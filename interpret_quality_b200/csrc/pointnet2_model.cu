@@ -82,13 +82,15 @@ protected:
             if (int rc = launch_ball_query(src_xyz, new_xyz, Bc, Nsrc, S, sc.radius, sc.K, gidx, st)) return rc;
             const int64_t rows = Bc * S * sc.K;
             if (engine == 1) {
-                if (int rc = launch_group_sub_act(U + sc.col1, sa.c1_total, V + sc.col1, sa.c1_total, sc.b1, gidx, Bc, S,
-                                                  sc.K, Nsrc, sc.c1, ACT_RELU, nullptr, h1hi, h1lo, sc.c1, st))
-                    return rc;
+                // layers 1 and 2 in one kernel: H1 = relu(U[idx] - V + b1) is produced tile by tile inside the GEMM that
+                // consumes it (gemm_tc.cu, gathered-A variant) and never written to HBM
                 TcGemm a;
-                a.A_hi = h1hi; a.A_lo = h1lo; a.lda = sc.c1; a.B_hi = sc.l2.w_hi; a.B_lo = sc.l2.w_lo; a.ldb = sc.c1;
+                a.gather.U = U + sc.col1; a.gather.ldu = sa.c1_total; a.gather.V = V + sc.col1; a.gather.ldv = sa.c1_total;
+                a.gather.bias = sc.b1; a.gather.idx = gidx; a.gather.K = sc.K; a.gather.S = S; a.gather.nsrc = Nsrc;
+                a.gather.act = ACT_RELU;
+                a.B_hi = sc.l2.w_hi; a.B_lo = sc.l2.w_lo; a.ldb = sc.c1;
                 a.K = sc.c1; a.M = (int)rows; a.N = sc.c2; a.C_hi = h2hi; a.C_lo = h2lo; a.ldc = sc.c2;
-                a.bias = sc.l2.b; a.act = ACT_RELU; a.tag = "tc_sa_mlp2";
+                a.bias = sc.l2.b; a.act = ACT_RELU; a.tag = "tc_sa_mlp12";
                 if (int rc = launch_gemm_tc(a, st)) return rc;
                 TcGemm b;
                 b.mode = 1;
