@@ -160,8 +160,9 @@ int launch_mask_interaction(const float *data, const float *center, const int64_
 
 // ------------------------------------------------------------------ reward
 // modified: z_y - logsumexp(z_{!=y})  (= log p/(1-p));  normal: log_softmax(z)_y.
-// exp / log through the SFU (ex2.approx / lg2.approx, ~2 ulp): with libm's expf / logf the 10 exponentials per row made
-// these kernels ALU-bound at 0.15 of the copy bandwidth; the rewards move by ~1e-7 of their scale.
+// libm expf / logf on purpose: interactions are differences of four rewards of magnitude ~10 that nearly cancel, and the
+// SFU forms (ex2.approx / lg2.approx) moved them by 1e-5 of their scale.  With 10 exact exponentials per 40 bytes these
+// kernels are ALU bound (0.15-0.3 of the copy bandwidth when timed alone); they are <0.05 % of a step.
 __device__ __forceinline__ float reward_of_row(const float *z, int C, int lbl, int softmax_normal)
 {
     float mx = -INFINITY;
@@ -169,9 +170,9 @@ __device__ __forceinline__ float reward_of_row(const float *z, int C, int lbl, i
         if (softmax_normal || c != lbl) mx = fmaxf(mx, z[c]);
     float s = 0.0f;
     for (int c = 0; c < C; ++c)
-        if (softmax_normal || c != lbl) s += __expf(z[c] - mx);
+        if (softmax_normal || c != lbl) s += expf(z[c] - mx);
     // log_softmax subtracts the max first; logsumexp adds it back last
-    return softmax_normal ? (z[lbl] - mx) - __logf(s) : z[lbl] - (__logf(s) + mx);
+    return softmax_normal ? (z[lbl] - mx) - logf(s) : z[lbl] - (logf(s) + mx);
 }
 
 // A row of logits is 40 bytes (160 for the 4 clouds of a context): read one row per thread, a warp touches 10-40 lines per
