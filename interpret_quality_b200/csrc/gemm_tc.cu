@@ -36,7 +36,7 @@ using namespace tc;
 namespace {
 
 constexpr int TC_THREADS = 192;
-constexpr int GA_THREADS = 256;          // gathered-A variant: two groups of four gather warps, alternating ring stages
+constexpr int GA_THREADS = 384;          // gathered-A variant: three groups of four gather warps taking ring stages in turn
 
 // Kernel parameters.  Together with the seven 128-byte tensor maps they must stay within 1024 bytes: one 64-byte field more
 // and every variant of the kernel ran 25-50 % slower on B200 (measured by padding this struct: PointNet conv+pool 10.5 ->
@@ -243,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             const int64_t cen = row / p.gK, cloud = cen / p.gS;
             const float *u = p.gU + (cloud * p.gnsrc + __ldg(p.gidx + row)) * p.gldu;
             const float *v = p.gV + cen * p.gldv;
-            for (int kb = 0; kb < kblocks; ++kb, turn ^= 1) {
+            for (int kb = 0; kb < kblocks; ++kb, turn = turn + 1 == GA_THREADS / 128 ? 0 : turn + 1) {
                 if (turn != grp) {                                    // the other group's stage
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     continue;
