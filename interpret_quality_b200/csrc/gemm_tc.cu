@@ -63,6 +63,9 @@ struct TcParams {
             int cout;
             int m_tiles;                 // ceil(Cout / 128)
             int points;                  // columns per group
+            int a_rows;                  // ATM variants: the A tile is parked in TMEM straight from global memory
+            const float *a_hi, *a_lo;
+            int64_t lda;
         };
         // gathered-A STORE: A[row][c] = act(U[cloud*nsrc + idx[row]][c] - V[row / gK][c] + gbias[c]), cloud = row / (gK * gS)
         struct {
@@ -75,9 +78,9 @@ struct TcParams {
 };
 static_assert(sizeof(TcParams) + 7 * 128 <= 1024, "kernel parameters must stay within 1 KB (see above)");
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool ATM = false>
 struct TcSmem {
-    static constexpr int A_BYTES = TBM * TBK * 4;
+    static constexpr int A_BYTES = ATM ? 0 : TBM * TBK * 4;                 // ATM: A lives in TMEM, the ring holds B only
     static constexpr int B_BYTES = BN * TBK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int BAR_BYTES = 256;
@@ -117,7 +120,7 @@ __device__ __forceinline__ void store_box(const CUtensorMap *map, const float (&
 // The epilogue variant is a template parameter (VAR_*): with run-time mode switches inside one kernel the compiler's
 // unswitching / unrolling choices for one variant moved whenever another was touched (POOL 85 -> 130 ms on PointNet++
 // after an unrelated edit).
-enum : int { VAR_STORE = 0, VAR_POOL_RUN = 1, VAR_POOL_TILE = 2, VAR_STORE_GATHER = 3 };
+enum : int { VAR_STORE = 0, VAR_POOL_RUN = 1, VAR_POOL_TILE = 2, VAR_STORE_GATHER = 3, VAR_POOL_RUN_ATM = 4, VAR_POOL_TILE_ATM = 5 };
 template <int BN, int STAGES, int VAR>
 __global__ void __launch_bounds__(TC_THREADS + (VAR == VAR_STORE_GATHER ? GA_THREADS : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
@@ -125,10 +128,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_chi,
                const __grid_constant__ CUtensorMap map_clo, const TcParams p)
 {
-    using S = TcSmem<BN, STAGES>;
+    // ATM ("A in tensor memory", POOL with K <= 128): a CTA keeps ONE 128-row tile of A -- the output channels it owns,
+    // hi and lo -- parked in TMEM for its whole life (the grid is a multiple of the number of row tiles, so all its units
+    // share it) and the MMAs read it from there; the ring carries B only, half the L2 operand stream of the SS form.
+    constexpr bool ATM = VAR == VAR_POOL_RUN_ATM || VAR == VAR_POOL_TILE_ATM;
+    using S = TcSmem<BN, STAGES, ATM>;
     constexpr bool GA = VAR == VAR_STORE_GATHER;
     constexpr bool STORE = VAR == VAR_STORE || VAR == VAR_STORE_GATHER;
-    constexpr bool POOL_RUN = VAR == VAR_POOL_RUN;                          // groups of >= BN columns: running reduction
+    constexpr bool POOL_RUN = VAR == VAR_POOL_RUN || VAR == VAR_POOL_RUN_ATM;   // groups of >= BN columns: running reduction
+    static_assert(!ATM || BN == 128, "the TMEM-resident A variants use 128-column tiles");
+    constexpr uint32_t TMEM_COLS = ATM ? 512u : (uint32_t)tmem_cols_for(BN);
+    constexpr uint32_t A_COL = 256;                                         // ATM: A hi at columns [256, 384), lo at [384, 512)
     constexpr uint32_t FULL_ARRIVALS = GA ? 5 : 1;                          // TMA producer (+ the four gather warps)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -137,7 +147,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full = empty_bar + STAGES;
     uint64_t *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *a_full = tmem_empty + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.K + TBK - 1) / TBK;          // TMA zero-fills the K tail
@@ -146,10 +157,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         prefetch_tmap(&map_ahi); prefetch_tmap(&map_alo); prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], FULL_ARRIVALS); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        mbar_init(a_full, 4);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, tmem_cols_for(BN));
+        tmem_alloc(tmem_ptr, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -183,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     uint8_t *st = smem + stage * S::STAGE_BYTES;
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&full_bar[stage], GA ? 2 * S::B_BYTES : S::STAGE_BYTES);
-                        if (!GA) {
+                        if (!GA && !ATM) {
                             tma_load_2d(st, &map_ahi, &full_bar[stage], kb * TBK, a_row0);
                             tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * TBK, a_row0);
                         }
@@ -198,6 +210,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         constexpr uint32_t idesc = make_idesc(BN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
+        if (ATM) {                                                          // the epilogue warps have parked this CTA's A tile
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+        }
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x)
             for (int j = 0; j < p.tiles_per_unit; ++j) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -218,7 +234,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
 #pragma unroll
                             for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
                                 const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                                umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
+                                if (ATM)
+                                    umma_tf32_ts(d_tmem, tmem_base + A_COL + (term == 0 ? 128u : 0u) + (uint32_t)(kb * TBK + ks * UMMA_K),
+                                                 bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
+                                else
+                                    umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
                             }
                         }
                         umma_commit(&empty_bar[stage]);                  // frees the stage when the MMAs retire
@@ -282,6 +302,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         const int row_in_tile = quad * 32 + lane;
         int acc = 0, nbox = 0;
         uint32_t acc_phase = 0;
+        if (ATM) {
+            // thread = row of the tile = output channel: K hi values to columns [A_COL, A_COL+K), K lo values 128 further
+            const int ch = (int)(blockIdx.x % p.m_tiles) * TBM + row_in_tile;
+            const uint32_t a_t = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL;
+            for (int half = 0; half < 2; ++half) {
+                const float4 *src = reinterpret_cast<const float4 *>((half ? p.a_lo : p.a_hi) + (int64_t)ch * p.lda);
+                for (int c = 0; c < kblocks; ++c) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (ch < p.a_rows && c * TBK + 4 * q < p.K) f = __ldg(src + c * 8 + q);
+                        r[4 * q] = __float_as_uint(f.x); r[4 * q + 1] = __float_as_uint(f.y);
+                        r[4 * q + 2] = __float_as_uint(f.z); r[4 * q + 3] = __float_as_uint(f.w);
+                    }
+                    tmem_st32(a_t + (uint32_t)(half * 128 + c * TBK), r);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             float run_max = -INFINITY, run_sum = 0.0f;
             int run_arg = 0;
@@ -370,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols_for(BN));
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -427,7 +470,8 @@ bool tc_gemm_supported(const TcGemm &g)
 template <int BN, int STAGES, int VAR>
 static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_t b_rows, cudaStream_t st)
 {
-    using S = TcSmem<BN, STAGES>;
+    constexpr bool ATM = VAR == VAR_POOL_RUN_ATM || VAR == VAR_POOL_TILE_ATM;
+    using S = TcSmem<BN, STAGES, ATM>;
     CUtensorMap mahi, malo, mbhi, mblo;
     if (int rc = make_map(&mbhi, g.B_hi, b_rows, g.K, g.ldb, BN)) return rc;
     if (int rc = make_map(&mblo, g.B_lo, b_rows, g.K, g.ldb, BN)) return rc;
@@ -452,7 +496,11 @@ static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_
         IQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
-    const int grid = std::min(p.num_units, sm_count());
+    int grid = std::min(p.num_units, sm_count());
+    if (ATM) {                                                  // a CTA keeps one row tile of A: grid = multiple of m_tiles
+        grid = std::max(p.m_tiles, grid / p.m_tiles * p.m_tiles);
+        p.a_hi = g.A_hi; p.a_lo = g.A_lo; p.lda = g.lda; p.a_rows = (int)a_rows;
+    }
     gemm_tc_kernel<BN, STAGES, VAR><<<grid, TC_THREADS + (GA ? GA_THREADS : 0), S::TOTAL, st>>>(mahi, malo, mbhi, mblo, mc, mchi, mclo, p);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
@@ -500,6 +548,9 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
         default: return launch_tc_variant<32, 4, VAR_STORE_GATHER>(g, p, a_rows, b_rows, st);
         }
     }
+    if (g.mode == 1 && g.K <= 128 && g.lda % 4 == 0 && p.m_tiles <= sm_count() && !getenv("IQ_TC_NO_ATM"))
+        return g.points >= bn ? launch_tc_variant<128, 6, VAR_POOL_RUN_ATM>(g, p, a_rows, b_rows, st)
+                              : launch_tc_variant<128, 6, VAR_POOL_TILE_ATM>(g, p, a_rows, b_rows, st);
     if (g.mode == 1)
         return g.points >= bn ? launch_tc_variant<128, 3, VAR_POOL_RUN>(g, p, a_rows, b_rows, st)
                               : launch_tc_variant<128, 3, VAR_POOL_TILE>(g, p, a_rows, b_rows, st);
