@@ -118,6 +118,7 @@ protected:
                 p.B_hi = L.wcat_hi; p.B_lo = L.wcat_lo; p.ldb = L.cin;
                 p.K = L.cin; p.M = (int)rows; p.N = 2 * L.cout; p.C = pq; p.ldc = 2 * L.cout; p.bias = L.bcat;
                 p.tag = "tc_edge_pq";
+                p.four_terms = (dynamic && l < 3) ? 1 : 0;      // upstream of a dynamic kNN (IQ_TC_ALL experiment): 4xTF32
                 if (int rc = launch_gemm_tc(p, st)) return rc;
             } else {
                 GemmDesc p;

@@ -51,6 +51,7 @@ struct TcParams {
     int out_c, out_hilo;         // STORE outputs present: fp32 and / or its tf32 hi/lo split
     float alpha;
     int dbg;                     // IQ_TC_DBG (scripts/tc_probe.py): 1 = STORE epilogue skips its math and stores
+    int four_terms;              // also accumulate Alo*Blo (the 2^-22 term 3xTF32 drops): fp32-FMA-chain accuracy
     const float *bias;           // STORE: per column (index b_row0 + c), POOL: per row (channel)
     union {
         // POOL: columns are grouped in runs of `points` consecutive B rows (points of a cloud / neighbours of a centroid).
@@ -227,6 +228,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     const uint64_t bhi = make_smem_desc(sbase + 2 * S::A_BYTES);
                     const uint64_t blo = make_smem_desc(sbase + 2 * S::A_BYTES + S::B_BYTES);
                     if (elect_one_sync()) {
+                        if (!ATM && p.four_terms) {
+#pragma unroll
+                            for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
+                                const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                                umma_tf32(d_tmem, alo + koff, blo + koff, idesc, (kb | ks) != 0 ? 1u : 0u);
+                            }
+                        }
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {            // small terms first
                             const uint64_t ad = term == 0 ? alo : ahi;
@@ -238,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                                     umma_tf32_ts(d_tmem, tmem_base + A_COL + (term == 0 ? 128u : 0u) + (uint32_t)(kb * TBK + ks * UMMA_K),
                                                  bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
                                 else
-                                    umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
+                                    umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks | p.four_terms) != 0 ? 1u : 0u);
                             }
                         }
                         umma_commit(&empty_bar[stage]);                  // frees the stage when the MMAs retire
@@ -512,7 +520,7 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
     ProfileScope _ps(g.tag, st);
     IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape");
     TcParams p = {};
-    p.K = g.K; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act;
+    p.K = g.K; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act; p.four_terms = g.four_terms;
     const char *dbg = getenv("IQ_TC_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
     int64_t a_rows, b_rows;

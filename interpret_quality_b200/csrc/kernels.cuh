@@ -73,6 +73,7 @@ struct TcGemm {
     float alpha = 1.0f;
     const float *bias = nullptr;  // STORE: per output column; POOL: per output channel
     int act = ACT_NONE;
+    int four_terms = 0;           // STORE: add the Alo*Blo term (4xTF32): the accuracy of an fp32 FMA chain
     const char *tag = "gemm_tc";
     // STORE only, optional: produce the A rows on the fly from a grouping instead of reading A_hi / A_lo,
     //   A[row][c] = act(U[cloud*nsrc + idx[row]][c] - V[row / K][c] + bias[c]),  cloud = row / (K * S)
