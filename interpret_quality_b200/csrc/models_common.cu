@@ -171,8 +171,8 @@ int64_t Model::workspace_bytes(int64_t B, int64_t N)
 int Model::forward(const float *x, int point_major, int64_t B, int64_t N, float *logits, void *wsp, int64_t ws_bytes,
                    float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st)
 {
+    if (B == 0) return 0;                                          // an empty batch has null tensors and nothing to do
     IQ_CHECK(x && logits, "forward: null input or output");
-    if (B == 0) return 0;
     IQ_CHECK(wsp, "forward: null workspace");
     Workspace ws;
     ws.base = reinterpret_cast<char *>(wsp);

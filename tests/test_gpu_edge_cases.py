@@ -1,0 +1,67 @@
+"""Edge cases of the CUDA path the reference's own usage reaches: the 40-class head (dataset modelnet40,
+models/dgcnn.py:56-58), wide logits rows in the reward / interaction kernels, single-cloud and empty batches."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from interpret_quality_b200 import ops, synthetic
+from interpret_quality_b200.tools import final_common, final_util
+from oracle import coalition, nets
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+R = 32
+
+
+def masked_clouds(n_perm=1):
+    from oracle import geom
+    data = synthetic.make_cloud(1024)
+    rid = geom.region_id(data[0], geom.fps(data, R)[0])
+    return geom.mask_shapley(data[0], coalition.center_of(data), synthetic.make_orders(n_perm, R), rid)
+
+
+@pytest.mark.parametrize("name", ["pointnet", "gcnn"])
+def test_forty_class_head(name):
+    a = types.SimpleNamespace(model=name, k=20, dataset="modelnet40", feature_transform=True, device=DEV)
+    sd = synthetic.make_state_dict(name, num_classes=40)
+    model = final_util.build_model(a, sd)
+    assert model.output_channels == 40
+    x = masked_clouds()[::4]                                            # 9 clouds
+    got = model.forward_point_major(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    want = nets.forward(name, torch.from_numpy(x).permute(0, 2, 1).contiguous(),
+                        {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}).numpy()
+    assert got.shape == (9, 40)
+    assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max()
+    for soft in ("modified", "normal"):
+        v = final_common.get_reward(torch.from_numpy(got).to(DEV), torch.tensor([17]), types.SimpleNamespace(softmax_type=soft))
+        ref = coalition.reward(torch.from_numpy(got), 17, soft).numpy()
+        assert np.abs(v.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_wide_rows_in_the_reduction_kernels():
+    """C = 40 and C = 100 logits rows: the shared-memory staging of reward_kernel / interaction_reduce_kernel."""
+    from interpret_quality_b200.final_cal_interactions import compute_order_interaction
+    rs = np.random.RandomState(4)
+    for C, lbl in ((40, 39), (100, 0)):
+        logits = (rs.normal(size=(3, 4 * 37, C)) * 3).astype(np.float32)
+        got = compute_order_interaction(torch.from_numpy(logits).to(DEV), torch.tensor([lbl]), types.SimpleNamespace(softmax_type="modified"))
+        v = coalition.reward(torch.from_numpy(logits.reshape(-1, C)), lbl, "modified").numpy().reshape(3, 37, 4)
+        want = (v[..., 0] + v[..., 3]) - v[..., 1] - v[..., 2]
+        assert got.shape == (3, 37) and np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-3)
+        r = ops.reward(torch.from_numpy(logits.reshape(-1, C)).to(DEV), lbl, "normal").cpu().numpy()
+        rr = coalition.reward(torch.from_numpy(logits.reshape(-1, C)), lbl, "normal").numpy()
+        assert np.abs(r - rr).max() <= 1e-5 * np.abs(rr).max()
+
+
+@pytest.mark.parametrize("name", ["dgcnn", "pointnet2"])
+def test_single_cloud_and_empty_batch(name):
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True, device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict(name))
+    x = torch.from_numpy(masked_clouds()[5:12]).to(DEV)
+    full = model.forward_point_major(x).cpu().numpy()
+    one = model.forward_point_major(x[3:4].contiguous()).cpu().numpy()
+    assert np.abs(one - full[3:4]).max() <= 1e-6 * np.abs(full).max()      # a cloud's logits do not depend on its batch
+    empty = model.forward_point_major(x[:0].contiguous())
+    assert tuple(empty.shape) == (0, 10)
