@@ -15,6 +15,8 @@
 //   agg              sum_j H3[j][c] * Wd[j][w]  -> (centroid, 16 C)   aggregate_kernel
 //   out              relu(bn(Linear(agg)))                             tcgen05 STORE (sa1, sa2) / head GEMM (sa3)
 // FPS and kNN depend on coordinates only, so no discrete decision sees the 3xTF32 arithmetic.
+#include <stdlib.h>
+
 #include "model.cuh"
 
 namespace iq {
@@ -303,7 +305,7 @@ protected:
         if (int rc = sgemm(new_xyz, 3, L.w1x, 3, nullptr, s.V, L.c1, cents, L.c1, 3, ACT_NONE, "sgemm_sa_centroid", st))
             return rc;
         const bool tc = engine == 1;
-        const bool fuse12 = tc && L.c2 <= 128 && rows % 128 == 0;   // layers 1 + 2 in one kernel (gemm_tc.cu, gathered A)
+        const bool fuse12 = tc && L.c2 <= 128 && rows % 128 == 0 && !getenv("IQ_TC_NO_GATHER");   // layers 1 + 2 in one kernel (gemm_tc.cu, gathered A)
         if (!fuse12)
             if (int rc = launch_group_sub_act(s.U, L.c1, s.V, L.c1, L.b1, s.idx, Bc, S, K, Nsrc, L.c1, ACT_RELU,
                                               tc ? nullptr : s.h1hi, tc ? s.h1hi : nullptr, tc ? s.h1lo : nullptr, L.c1, st))

@@ -14,6 +14,8 @@
 //   sa3: 643 -> 256 -> 512 -> 1024 on the 128 remaining points, max over them (fp32 SIMT + pooling epilogue)
 // FPS and ball queries depend on coordinates only, so the MLPs can all run in 3xTF32 without touching any
 // discrete decision.
+#include <stdlib.h>
+
 #include "model.cuh"
 
 namespace iq {
@@ -83,11 +85,19 @@ protected:
             const int64_t rows = Bc * S * sc.K;
             if (engine == 1) {
                 // layers 1 and 2 in one kernel: H1 = relu(U[idx] - V + b1) is produced tile by tile inside the GEMM that
-                // consumes it (gemm_tc.cu, gathered-A variant) and never written to HBM
+                // consumes it (gemm_tc.cu, gathered-A variant) and never written to HBM.  IQ_TC_NO_GATHER (tests) takes the
+                // two-kernel route through H1; the results are bitwise the same.
                 TcGemm a;
-                a.gather.U = U + sc.col1; a.gather.ldu = sa.c1_total; a.gather.V = V + sc.col1; a.gather.ldv = sa.c1_total;
-                a.gather.bias = sc.b1; a.gather.idx = gidx; a.gather.K = sc.K; a.gather.S = S; a.gather.nsrc = Nsrc;
-                a.gather.act = ACT_RELU;
+                if (getenv("IQ_TC_NO_GATHER")) {
+                    if (int rc = launch_group_sub_act(U + sc.col1, sa.c1_total, V + sc.col1, sa.c1_total, sc.b1, gidx, Bc, S,
+                                                      sc.K, Nsrc, sc.c1, ACT_RELU, nullptr, h1hi, h1lo, sc.c1, st))
+                        return rc;
+                    a.A_hi = h1hi; a.A_lo = h1lo; a.lda = sc.c1;
+                } else {
+                    a.gather.U = U + sc.col1; a.gather.ldu = sa.c1_total; a.gather.V = V + sc.col1; a.gather.ldv = sa.c1_total;
+                    a.gather.bias = sc.b1; a.gather.idx = gidx; a.gather.K = sc.K; a.gather.S = S; a.gather.nsrc = Nsrc;
+                    a.gather.act = ACT_RELU;
+                }
                 a.B_hi = sc.l2.w_hi; a.B_lo = sc.l2.w_lo; a.ldb = sc.c1;
                 a.K = sc.c1; a.M = (int)rows; a.N = sc.c2; a.C_hi = h2hi; a.C_lo = h2lo; a.ldc = sc.c2;
                 a.bias = sc.l2.b; a.act = ACT_RELU; a.tag = "tc_sa_mlp12";

@@ -65,3 +65,15 @@ def test_single_cloud_and_empty_batch(name):
     assert np.abs(one - full[3:4]).max() <= 1e-6 * np.abs(full).max()      # a cloud's logits do not depend on its batch
     empty = model.forward_point_major(x[:0].contiguous())
     assert tuple(empty.shape) == (0, 10)
+
+
+@pytest.mark.parametrize("name", ["pointnet2", "pointconv"])
+def test_gathered_a_gemm_is_bitwise_the_two_kernel_route(name, monkeypatch):
+    """Grouped-MLP layers 1+2 fused in the tcgen05 GEMM (gathered A) against group_sub_act + GEMM through HBM."""
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True, device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict(name))
+    x = torch.from_numpy(masked_clouds()[3:17]).to(DEV)
+    fused = model.forward_point_major(x).clone()
+    monkeypatch.setenv("IQ_TC_NO_GATHER", "1")
+    unfused = model.forward_point_major(x).clone()
+    assert torch.equal(fused, unfused)
