@@ -77,3 +77,16 @@ def test_gathered_a_gemm_is_bitwise_the_two_kernel_route(name, monkeypatch):
     monkeypatch.setenv("IQ_TC_NO_GATHER", "1")
     unfused = model.forward_point_major(x).clone()
     assert torch.equal(fused, unfused)
+
+
+@pytest.mark.parametrize("k", [5, 12])
+def test_dgcnn_other_neighbourhood_sizes(k):
+    """args.k other than the default 20 (models/dgcnn.py:55): fused kNN, re-rank and gather take k at run time."""
+    a = types.SimpleNamespace(model="dgcnn", k=k, dataset="shapenet", device=DEV)
+    sd = synthetic.make_state_dict("dgcnn")
+    model = final_util.build_model(a, sd)
+    x = masked_clouds()[::5]                                            # 7 clouds, from fully masked to untouched
+    got = model.forward_point_major(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    want = nets.forward("dgcnn", torch.from_numpy(x).permute(0, 2, 1).contiguous(),
+                        {kk: torch.from_numpy(np.asarray(v)) for kk, v in sd.items()}, k=k).numpy()
+    assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max()
