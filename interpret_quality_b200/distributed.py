@@ -75,3 +75,25 @@ def interactions_sharded(logits_fn, reduce_fn, num_pairs, group=None):
     out = out * mask
     allreduce_sum_(out, group)
     return out.detach().cpu().numpy()
+
+
+def poses_sharded(pose_fn, n_pose, num_regions, rows, channels, device, group=None, on_pose=None):
+    """Pose axis of the enumeration runner (tools/final_common.py:150-166 of the reference loops it serially).
+
+    pose_fn(i) -> (phi (R,) float64 ndarray, logits (rows, C) float32 tensor) for pose i.  Poses are dealt
+    round-robin (rank, rank+world, ...) so that neighbouring, similarly expensive poses spread over the ranks;
+    every rank fills its own rows of zero-initialised (n_pose, R) float64 / (n_pose, rows, C) float32 slabs and
+    one allreduce per slab makes them complete on every rank.  on_pose(i, phi) is called after each local pose
+    (the runner's per-pose log line at world size 1).  Returns (shap, all_logits) tensors on `device`."""
+    rank, world = _world(group)
+    shap = torch.zeros((n_pose, num_regions), dtype=torch.float64, device=device)
+    all_logits = torch.zeros((n_pose, rows, channels), dtype=torch.float32, device=device)
+    for i in range(rank, n_pose, world):
+        phi, logits = pose_fn(i)
+        shap[i] = torch.as_tensor(np.asarray(phi, dtype=np.float64)).to(device)
+        all_logits[i] = logits
+        if on_pose is not None:
+            on_pose(i, phi)
+    allreduce_sum_(shap, group)
+    allreduce_sum_(all_logits, group)
+    return shap, all_logits

@@ -107,6 +107,7 @@ def test(args, get_transform_params_fn, disturb_fn, print_info_fn, save_info_fn,
     combined by one allreduce of disjoint zero-initialised slabs; rank 0 writes the files."""
     import time
     import torch.distributed as dist
+    from ..distributed import poses_sharded
     from .final_util import IOStream, load_model, mkdir
     if samples is None:
         raise ValueError("test(): pass samples=[(data, lbl, folder_name), ...]; the reference's dataset loaders "
@@ -140,20 +141,16 @@ def test(args, get_transform_params_fn, disturb_fn, print_info_fn, save_info_fn,
         all_transform_params = get_transform_params_fn(args, data.device)
         n_pose = all_transform_params.size()[0]
         rows = args.num_samples * (args.num_regions + 1)
-        shap = torch.zeros((n_pose, args.num_regions), dtype=torch.float64, device=dev)
-        all_logits = torch.zeros((n_pose, rows, model.output_channels), dtype=torch.float32, device=dev)
-        for i in range(rank, n_pose, world):
-            transform_param = all_transform_params[i]
-            data_disturb = disturb_fn(data, transform_param)
-            region_shap_value, logits_this_pose = shap_sampling_all_regions_batch(model, data_disturb, lbl, region_id,
-                                                                                  load_order_list, args)
-            shap[i] = torch.from_numpy(region_shap_value).to(dev)
-            all_logits[i] = logits_this_pose
+        def pose_fn(i):
+            data_disturb = disturb_fn(data, all_transform_params[i])
+            return shap_sampling_all_regions_batch(model, data_disturb, lbl, region_id, load_order_list, args)
+
+        def on_pose(i, region_shap_value):
             if io and world == 1:
-                print_info_fn(io, transform_param, region_shap_value, i)
-        if world > 1:
-            dist.all_reduce(shap)
-            dist.all_reduce(all_logits)
+                print_info_fn(io, all_transform_params[i], region_shap_value, i)
+
+        shap, all_logits = poses_sharded(pose_fn, n_pose, args.num_regions, rows, model.output_channels, dev,
+                                         on_pose=on_pose)
         if rank == 0:
             region_shapley_list = shap.cpu().numpy()
             if world > 1:

@@ -90,3 +90,39 @@ def test_two_ranks_gloo_match_the_unsharded_reference(tmp_path):
     g = np.load(os.path.join(GOLDEN, "pointnet.npz"))
     assert np.abs(res["phi"] - g["shapley_phi"]).max() <= 1e-6 * np.abs(g["shapley_phi"]).max()
     assert np.abs(res["inter"] - g["inter_m3"]).max() <= 1e-5 * max(np.abs(g["inter_m3"]).max(), 1e-3)
+
+
+def _pose_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        seen = []
+
+        def pose_fn(i):
+            seen.append(i)
+            return np.arange(R, dtype=np.float64) * (i + 1), torch.full((6, 4), float(i + 1))
+
+        logged = []
+        shap, logits = iqd.poses_sharded(pose_fn, 7, R, 6, 4, torch.device("cpu"),
+                                         on_pose=lambda i, phi: logged.append(i))
+        assert seen == list(range(rank, 7, world)) == logged        # round-robin deal, whole poses per rank
+        assert shap.dtype == torch.float64 and logits.dtype == torch.float32
+        np.savez(out % rank, shap=shap.numpy(), logits=logits.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_poses_dealt_round_robin_and_complete_on_every_rank(tmp_path):
+    out = str(tmp_path / "pose%d.npz")
+    mp.spawn(_pose_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    want_shap = np.arange(R)[None, :] * np.arange(1, 8)[:, None]
+    for rank in range(2):
+        res = np.load(out % rank)
+        assert np.array_equal(res["shap"], want_shap)
+        assert np.array_equal(res["logits"], np.broadcast_to(np.arange(1, 8, dtype=np.float32)[:, None, None], (7, 6, 4)))
+
+
+def test_poses_world_size_one_is_the_serial_loop():
+    shap, logits = iqd.poses_sharded(lambda i: (np.full(R, i, dtype=np.float64), torch.zeros(2, 3)), 3, R, 2, 3,
+                                     torch.device("cpu"))
+    assert np.array_equal(shap.numpy()[:, 0], [0.0, 1.0, 2.0]) and logits.shape == (3, 2, 3)
