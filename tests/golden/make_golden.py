@@ -195,7 +195,7 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run"):
+        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -298,3 +298,59 @@ def shap_run():
 
 if __name__ == "__main__" and "shap_run" in sys.argv[1:]:
     shap_run()
+
+
+def result_tables():
+    """result_tables.npz: the reference's final_result.py table code (cal_sensitivity :83-102, cal_correlation_coef
+    :124-140, cal_shapley_smoothness_metric_single_pc :144-176) on seeded (poses, R) value arrays laid out in the
+    reference's folders.  matplotlib is not installed here and final_result.py only needs it for its plots, so the
+    import is satisfied by empty stand-in modules; no plotting function is called."""
+    import tempfile
+    from unittest import mock
+    for name in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d", "matplotlib.ticker",
+                 "matplotlib.patches", "matplotlib.colors", "matplotlib.cm"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    import final_result as ref_res
+    ref_res.num_regions, ref_res.num_points = R, 1024
+    rng = np.random.RandomState(7)
+    names = ["cloud%d" % i for i in range(4)]
+    d = tempfile.mkdtemp() + "/"
+    out = {}
+    data, fps_idx, region_id = base_inputs(1024)
+    for ci, name in enumerate(names):
+        base = d + name + "/"
+        # values with a per-region scale so that sensitivity and mean intensity correlate like real runs
+        scale = rng.gamma(2.0, 0.05, size=R)
+        for mode, n_pose in (("scale", 30), ("rotate", 24)):
+            os.makedirs(base + "%s_all/" % mode)
+            v = rng.randn(n_pose, R) * scale + rng.randn(R) * 0.02
+            np.save(base + "%s_all/region_shapley_value.npy" % mode, v)
+            out["%s_%s_values" % (name, mode)] = v
+        for direction, n_pose in (("inc", 5), ("dec", 7)):
+            os.makedirs(base + "linearity_all/allregion_%s/" % direction)
+            v = rng.randn(n_pose, R) * scale
+            np.save(base + "linearity_all/allregion_%s/region_shapley_value.npy" % direction, v)
+            out["%s_linearity_%s_values" % (name, direction)] = v
+        np.save(base + "region_id.npy", region_id)
+        for mode in ("scale", "rotate", "linearity"):
+            out["%s_%s_sensitivity" % (name, mode)] = ref_res.cal_sensitivity(base, mode)
+        m, m_poses, den = ref_res.cal_shapley_smoothness_metric_single_pc(
+            data[0].numpy(), out["%s_rotate_values" % name], region_id)
+        out["%s_smooth" % name] = np.array([m, den])
+        out["%s_smooth_poses" % name] = m_poses
+    # Table 3 through the reference's own function: it reads a global namespace and the sample-name list
+    ref_res.args = types.SimpleNamespace(dataset="shapenet")
+    ref_res.num_pc = len(names)
+    ref_res.get_exp_folder_name = lambda model_name, dataset: d
+    ref_res.get_folder_name_list = lambda a: names
+    for mode in ("scale", "rotate"):
+        out["pearson_mean_%s" % mode] = np.array(ref_res.cal_correlation_coef("pointnet", mode))
+        out["sens_all_%s" % mode] = ref_res.cal_sensitivity_all_pc("pointnet", mode)
+        out["intensity_all_%s" % mode] = ref_res.cal_mean_sv_intensity("pointnet", mode)
+    out["region_id"] = region_id
+    np.savez_compressed(os.path.join(HERE, "result_tables.npz"), **out)
+    print("result_tables.npz written", len(out), "arrays")
+
+
+if __name__ == "__main__" and "result_tables" in sys.argv[1:]:
+    result_tables()

@@ -87,4 +87,9 @@ def test_runner_writes_the_reference_files_and_values(golden, tmp_path):
     for i in range(3):
         assert np.abs(phi[i] - want[i]).max() <= 1e-3 * np.abs(want[i]).max()
     assert os.path.exists(out + "log.txt")
+    # the reference's table code (final_result.py:83-102) consumes these files unchanged
+    from interpret_quality_b200 import final_result
+    sens = final_result.cal_sensitivity(folder, "scale")
+    want_sens = final_result.sensitivity_of(want)
+    assert sens.shape == (R,) and np.abs(sens - want_sens).max() <= 2e-3 * want_sens.max()
     _ = ops
