@@ -159,6 +159,25 @@ int iq_linear_pool(const float *x_dev, const float *w_dev, const float *b_dev, i
                    int64_t N, int64_t K, int act, int engine, float *out_max_dev, float *out_mean_dev,
                    int64_t *out_arg_dev, void *stream);
 
+/* One epoch of the geometry ascent / descent of final_smoothness_center_enum_all.py: update_region :184-243 for every
+ * region whose alive flag is set (the loop over regions at :305-321), in one launch, a CTA per region.
+ *   data (N,3) in/out, data_orig (N,3): the cloud being pushed and the undisturbed cloud;
+ *   region_offsets (R+1) i32, region_members (N) i32: the points of region r are region_members[offsets[r]..offsets[r+1]),
+ *     in ascending point order (the order of data[:, region_id == r, :]); every region needs >= 2 points;
+ *   orient (R,3,3): rows o1,o2,o3 of cal_principal_orientation :22-45; var_ub / var_lb (R,3): set_var_bound :75-80;
+ *   smoothness (R) f64 in/out: the value of the last epoch in, the value measured before the last step out;
+ *   alive (R) i32 in/out: if_update; iters (R) i32 out; last_var (R,3) f32 out: var1..3 of the last step (:240);
+ *   stop_flags (R) i32 out: bit 0 too many points beyond dist_threshold, bit 1 no gradient, bit 2 max_iteration;
+ *   mode 0 linearity / 1 planarity / 2 scattering; rising 1 = "inc", 0 = "dec";
+ *   clamp 0 = the reference's behaviour (points beyond dist_threshold are counted, its pull-back :118 is a no-op on a
+ *   temporary view), 1 = pull them back onto the dist_threshold sphere as :103-120 describes. */
+int iq_region_smoothness_epoch(float *data_dev, const float *data_orig_dev, const int32_t *region_offsets_dev,
+                               const int32_t *region_members_dev, const float *orient_dev, const float *var_ub_dev,
+                               const float *var_lb_dev, double *smoothness_dev, int32_t *alive_dev, int32_t *iters_dev,
+                               float *last_var_dev, int32_t *stop_flags_dev, int64_t N, int64_t R, int64_t max_region,
+                               int mode, int rising, double step, double enum_step, double dist_threshold,
+                               double stop_ratio, int max_iteration, int clamp, void *stream);
+
 /* GEMM engine of the masked forward: 1 = tcgen05 3xTF32 (default), 0 = exact fp32 SIMT. */
 int iq_model_set_engine(iq_model *m, int engine);
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "iq_ball_query": (_int, [_vp, _vp, _i64, _i64, _i64, ctypes.c_double, _int, _vp, _vp]),
     "iq_knn_xyz": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "iq_knn_features": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),
+    "iq_region_smoothness_epoch": (_int, [_vp] * 12 + [_i64, _i64, _i64, _int, _int, ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_double, ctypes.c_double, _int, _int, _vp]),
     "iq_topk_rows": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "iq_linear": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "iq_linear_pool": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp]),

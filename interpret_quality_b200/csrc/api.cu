@@ -187,6 +187,22 @@ int iq_knn_features(const float *x, int64_t B, int64_t N, int64_t C, int k, int3
     return rc;
 }
 
+int iq_region_smoothness_epoch(float *data, const float *data_orig, const int32_t *offsets, const int32_t *members,
+                               const float *orient, const float *var_ub, const float *var_lb, double *smooth, int32_t *alive,
+                               int32_t *iters, float *last_var, int32_t *stop_flags, int64_t N, int64_t R, int64_t max_region,
+                               int mode, int rising, double step, double enum_step, double dist_threshold, double stop_ratio,
+                               int max_iteration, int clamp, void *stream)
+{
+    if (R == 0) return 0;
+    IQ_CHECK(data && data_orig && offsets && members && orient && var_ub && var_lb && smooth && alive && iters && last_var &&
+                 stop_flags,
+             "iq_region_smoothness_epoch: null pointer");
+    IQ_CHECK(N >= 2 && max_region <= N, "iq_region_smoothness_epoch: max_region exceeds the cloud");
+    return launch_region_smoothness_epoch(data, data_orig, offsets, members, orient, var_ub, var_lb, smooth, alive, iters,
+                                          last_var, stop_flags, R, max_region, mode, rising, step, enum_step, dist_threshold,
+                                          stop_ratio, max_iteration, clamp, as_stream(stream));
+}
+
 int iq_topk_rows(const float *keys, int64_t rows, int64_t N, int64_t ld, int k, int largest, int32_t *idx, void *stream)
 {
     IQ_CHECK(keys && idx, "iq_topk_rows: null pointer");

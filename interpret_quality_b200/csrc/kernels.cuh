@@ -126,4 +126,11 @@ int launch_group_max(const float *in, int64_t ld, int64_t groups, int K, int C, 
 int launch_copy_cols(const float *src, int64_t lds, int64_t rows, int cols, float *dst, int64_t ldd, int pad_to,
                      cudaStream_t st);
 
+// smoothness.cu
+int launch_region_smoothness_epoch(float *data, const float *data_orig, const int32_t *offsets, const int32_t *members,
+                                   const float *orient, const float *var_ub, const float *var_lb, double *smooth,
+                                   int32_t *alive, int32_t *iters, float *last_var, int32_t *stop_flags, int64_t R,
+                                   int64_t max_region, int mode, int rising, double step, double enum_step, double dist_thr,
+                                   double stop_ratio, int max_iteration, int clamp, cudaStream_t st);
+
 }  // namespace iq

@@ -163,6 +163,41 @@ def knn_features(x, k, return_counts=False):
     return (out, cnt) if return_counts else out
 
 
+SMOOTHNESS_MODES = {"linearity": 0, "planarity": 1, "scattering": 2}
+
+
+def region_smoothness_epoch(data, data_orig, offsets, members, orient, var_ub, var_lb, smoothness, alive, max_region, mode,
+                            objective, step, enum_step, dist_threshold, stop_ratio, max_iteration, clamp=False):
+    """One epoch of the geometry ascent / descent over every region whose `alive` flag is set
+    (final_smoothness_center_enum_all.py:184-243, :305-321), csrc/smoothness.cu.  data (N,3) is updated in place,
+    smoothness (R) float64 and alive (R) int32 too.  Returns (iters (R) int32, last_var (R,3) float32,
+    stop_flags (R) int32), all on the device."""
+    _chk(data, torch.float32, "data")
+    _chk(data_orig, torch.float32, "data_orig")
+    _chk(offsets, torch.int32, "offsets")
+    _chk(members, torch.int32, "members")
+    _chk(orient, torch.float32, "orient")
+    _chk(var_ub, torch.float32, "var_ub")
+    _chk(var_lb, torch.float32, "var_lb")
+    _chk(smoothness, torch.float64, "smoothness")
+    _chk(alive, torch.int32, "alive")
+    N, R = data.shape[0], offsets.shape[0] - 1
+    if data.shape != (N, 3) or data_orig.shape != (N, 3) or members.shape[0] != N:
+        raise ValueError("region_smoothness_epoch: data / data_orig must be (N,3) and members (N,)")
+    if orient.shape != (R, 3, 3) or var_ub.shape != (R, 3) or var_lb.shape != (R, 3) or smoothness.shape != (R,) \
+            or alive.shape != (R,):
+        raise ValueError("region_smoothness_epoch: per-region arrays must have %d rows" % R)
+    iters = torch.empty((R,), dtype=torch.int32, device=data.device)
+    last_var = torch.zeros((R, 3), dtype=torch.float32, device=data.device)
+    flags = torch.zeros((R,), dtype=torch.int32, device=data.device)
+    _lib.check(_lib.load().iq_region_smoothness_epoch(
+        data.data_ptr(), data_orig.data_ptr(), offsets.data_ptr(), members.data_ptr(), orient.data_ptr(), var_ub.data_ptr(),
+        var_lb.data_ptr(), smoothness.data_ptr(), alive.data_ptr(), iters.data_ptr(), last_var.data_ptr(), flags.data_ptr(),
+        N, R, int(max_region), SMOOTHNESS_MODES[mode], 1 if objective == "inc" else 0, float(step), float(enum_step),
+        float(dist_threshold), float(stop_ratio), int(max_iteration), 1 if clamp else 0, _stream()))
+    return iters, last_var, flags
+
+
 def topk_rows(keys, k, largest=True):
     """keys (rows,N) -> (rows,k) int32, unordered exact top-k with lowest-index tie-breaking."""
     _chk(keys, torch.float32, "keys")

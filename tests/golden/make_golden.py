@@ -195,7 +195,7 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables"):
+        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables", "smoothness"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -354,3 +354,70 @@ def result_tables():
 
 if __name__ == "__main__" and "result_tables" in sys.argv[1:]:
     result_tables()
+
+
+def smoothness():
+    """smoothness.npz: the reference's final_smoothness_center_enum_all.test_all_region (:281-350) on the synthetic cloud
+    (PointNet, CPU, 3 epochs, 4 permutations) for the three modes and both objectives: the cloud after every epoch,
+    the per-region smoothness, the Shapley values, and the per-region original info of get_original_region_info
+    (:245-268).  torch.symeig (:41) no longer exists in this torch; it is provided here as a thin forwarder to
+    torch.linalg.eigh (same ascending eigenvalue order, eigenvectors in columns), the reference file is unmodified."""
+    import tempfile
+    if not hasattr(torch, "symeig") or True:
+        torch.symeig = lambda A, eigenvectors=True: torch.linalg.eigh(A)
+    sys.modules.setdefault("final_data_shapley", types.ModuleType("final_data_shapley"))
+    for nm in ("ModelNet_Loader_Shapley_test", "ShapeNetDataset_Shapley_test"):
+        setattr(sys.modules["final_data_shapley"], nm, getattr(sys.modules["final_data_shapley"], nm, None))
+    import final_smoothness_center_enum_all as ref_sm
+    import time
+    data, fps_idx, region_id = base_inputs(1024)
+    model, margs = load_ref_model("pointnet")
+    orders = synthetic.make_orders(8, R)
+    out = {}
+    d = tempfile.mkdtemp() + "/"
+    for mode in ("linearity", "planarity", "scattering"):
+        a = types.SimpleNamespace(num_points=1024, num_regions=R, shapley_batch_size=2, num_samples=4,
+                                  softmax_type="modified", model="pointnet", device=torch.device("cpu"), mode=mode,
+                                  step=ref_sm.STEP, enum_step=ref_sm.ENUM_STEP, epoch=3, var_threshold=ref_sm.VAR_THRESHOLD,
+                                  dist_threshold=ref_sm.DIST_THRESHOLD, stop_ratio=ref_sm.STOP_RATIO,
+                                  max_iteration=ref_sm.MAX_ITERATION)
+        for objective in ("inc", "dec"):
+            t0 = time.time()
+            # data_list (:325) holds `data_copy.cpu().numpy()`: on a CPU run that aliases data_copy, so every saved
+            # epoch shows the final cloud (on CUDA .cpu() copies).  The per-epoch clouds are therefore recorded from
+            # the argument of the sampler call that follows each epoch (:328), through a recording wrapper.
+            seen = []
+
+            def recording_sampler(model_, data_, *rest, _inner=ref_common.shap_sampling_all_regions_batch):
+                seen.append(data_.detach().clone().numpy())
+                return _inner(model_, data_, *rest)
+
+            ref_sm.shap_sampling_all_regions_batch = recording_sampler
+            ref_sm.test_all_region(model, data, torch.tensor([LBL]), orders, region_id, d + mode + "_all/", a, objective)
+            p = d + mode + "_all/allregion_%s/" % objective
+            key = "%s_%s_" % (mode, objective)
+            out[key + "data"] = np.stack(seen[1:])                       # seen[0] is the undisturbed cloud (:299)
+            assert np.array_equal(out[key + "data"][-1], np.load(p + "data_smoothness.npy")[-1])
+            out[key + "smoothness"] = np.load(p + "%s.npy" % mode)
+            out[key + "phi"] = np.load(p + "region_shapley_value.npy")
+            out[key + "orig_phi"] = np.load(p + "orig_shapley_value.npy")
+            print(mode, objective, "epochs", out[key + "data"].shape[0], "%.1fs" % (time.time() - t0))
+    class _Quiet:
+        def cprint(self, text):
+            pass
+    orient, bounds, smooth0 = [], [], []
+    a.mode = "linearity"
+    for i in range(R):
+        _, s0, o, b = ref_sm.get_original_region_info(data, region_id, i, _Quiet(), a)
+        orient.append(torch.stack(o).numpy())
+        bounds.append(np.array([float(x) for x in b], dtype=np.float32))
+        smooth0.append(s0)
+    out["orientations"] = np.stack(orient)           # (R,3,3): rows o1,o2,o3
+    out["bounds"] = np.stack(bounds)                 # (R,6): ub1..3, lb1..3
+    out["linearity_orig"] = np.array(smooth0)
+    np.savez_compressed(os.path.join(HERE, "smoothness.npz"), **out)
+    print("smoothness.npz written")
+
+
+if __name__ == "__main__" and "smoothness" in sys.argv[1:]:
+    smoothness()
