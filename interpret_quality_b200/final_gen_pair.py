@@ -95,3 +95,95 @@ def check_adv_success(args, disturb_fn, samples=None, model=None):
             np.save(interaction_folder + "%s_adv/transform_params.npy" % args.mode, all_transform_params[pose_idx])
             results.append((num_miscls, pose_idx))
     return results
+
+
+# ---- folder walkers (save_pair_random :302-320, save_pair_single_region :145-218, save_context :45-71,
+# ---- save_pred_label :90-123).  The reference walks a global folder_name_list / its dataset loaders; here the cloud
+# ---- folder names (or `samples`) are arguments.
+
+def _folders(args, name):
+    base_folder = args.exp_folder + "%s/" % name
+    interaction_folder = base_folder + "interaction_seed%d/" % args.seed
+    return base_folder, interaction_folder, interaction_folder + "%s_adv_single_region/" % args.mode
+
+
+def _region_folders(single_region_folder):
+    """Sub-folders range_rank<rr>_region<ii>/ of a cloud's single-region folder, sorted by name like the reference."""
+    import os
+    return [single_region_folder + d + "/" for d in sorted(os.listdir(single_region_folder))
+            if os.path.isdir(single_region_folder + d)]
+
+
+def save_pair_random(args, folder_name_list):
+    """region_pair_list.npy (num_pairs_random, 2) per cloud under interaction_seed<seed>/, shared by the normal and
+    the adversarial pose; creates normal/ and <mode>_adv/.  One gen_pair_random draw per cloud, in list order."""
+    for name in folder_name_list:
+        _, interaction_folder, _ = _folders(args, name)
+        mkdir(interaction_folder + "normal/")
+        mkdir(interaction_folder + "%s_adv/" % args.mode)
+        np.save(interaction_folder + "region_pair_list.npy", gen_pair_random(args))
+
+
+def gen_pair_single_region(region, neighbor_idx, args):
+    """(num_neighbors, 2) pairs (region, j) over the ball-query neighbours j != region (:127-142); an empty (0,)
+    array when the region has no neighbour, like np.array([])."""
+    neighbors = np.nonzero(neighbor_idx[region])[0]
+    return np.array([[region, j] for j in neighbors if j != region])
+
+
+def save_pair_single_region(args, samples):
+    """Per cloud and region: the poses of its largest / smallest Shapley value over the enumeration written by
+    tools.final_common.test (<mode>_all/region_shapley_value.npy + trans_vector.npy / angle_tuple.npy) and the pairs
+    with its neighbouring regions, under <mode>_adv_single_region/range_rank<rr>_region<ii>/{normal,max_pose,min_pose}/.
+    range_rank 1 is the region whose value varies most over the poses.  Returns the last region_pair_list."""
+    from .final_result import BALL_QUERY_COEF, ball_query, square_distance_np
+    from .tools.final_util import cal_rank
+    assert args.mode == "trans" or args.mode == "rotate"
+    region_pair_list = None
+    for data, _, name in samples:
+        data = np.asarray(data.cpu() if hasattr(data, "cpu") else data).reshape(-1, 3)
+        base_folder, _, single_region_folder = _folders(args, name)
+        mode_folder = base_folder + "%s_all/" % args.mode
+        mkdir(single_region_folder)
+        region_id = np.load(base_folder + "region_id.npy")
+        values = np.load(mode_folder + "region_shapley_value.npy")                     # (poses, R)
+        transform_params = np.load(mode_folder + ("trans_vector.npy" if args.mode == "trans" else "angle_tuple.npy"))
+        max_pose_idx, min_pose_idx = np.argmax(values, axis=0), np.argmin(values, axis=0)
+        range_rank = args.num_regions - cal_rank(values.max(axis=0) - values.min(axis=0))
+        diameter = np.sqrt(np.maximum(square_distance_np(data), 0)).max()
+        centers = np.zeros((args.num_regions, 3))
+        for i in range(args.num_regions):
+            centers[i] = data[region_id == i].mean(axis=0)
+        neighbor_idx = ball_query(centers, r=BALL_QUERY_COEF * diameter)
+        for region in range(args.num_regions):
+            region_folder = single_region_folder + "range_rank%02d_region%02d/" % (range_rank[region], region)
+            for sub in ("normal/", "max_pose/", "min_pose/"):
+                mkdir(region_folder + sub)
+            for sub, pose in (("max_pose/", max_pose_idx[region]), ("min_pose/", min_pose_idx[region])):
+                np.save(region_folder + sub + "transform_params.npy", transform_params[pose])
+                np.save(region_folder + sub + "pose_idx.npy", pose)
+            region_pair_list = gen_pair_single_region(region, neighbor_idx, args)
+            np.save(region_folder + "region_pair_list.npy", region_pair_list)
+    return region_pair_list
+
+
+def save_context(args, folder_name_list):
+    """Contexts for the random pairs of every cloud, then for every single-region pair list (sorted folder order):
+    the numpy stream is consumed in exactly the reference's order."""
+    for name in folder_name_list:
+        _, interaction_folder, single_region_folder = _folders(args, name)
+        gen_context(np.load(interaction_folder + "region_pair_list.npy"), interaction_folder, args)
+        for region_folder in _region_folders(single_region_folder):
+            gen_context(np.load(region_folder + "region_pair_list.npy"), region_folder, args)
+
+
+def save_pred_label(args, disturb_fn, samples, model=None):
+    """pred_labels.{txt,npy} for the adversarial pose and for every region's max / min pose."""
+    if model is None:
+        model = load_model(args)
+    for data, lbl, name in samples:
+        _, interaction_folder, single_region_folder = _folders(args, name)
+        gen_pred_label(model, data, lbl, disturb_fn, interaction_folder + "%s_adv/" % args.mode, args)
+        for region_folder in _region_folders(single_region_folder):
+            gen_pred_label(model, data, lbl, disturb_fn, region_folder + "max_pose/", args)
+            gen_pred_label(model, data, lbl, disturb_fn, region_folder + "min_pose/", args)

@@ -55,3 +55,35 @@ def save_logits_all_orders(model, data, region_id, save_path, args):
         context_list = np.load(save_path + "../ratio%d_context_list.npy" % (int(ratio * 100)))
         all_logits = compute_order_interaction_logits(model, data, region_id, region_pair_list, context_list, args)
         torch.save(all_logits, save_path + "ratio%d_all_logits.pt" % (int(ratio * 100)))
+
+
+def save_logits(args, disturb_fn, samples, model=None, selected_sample_idx=None):
+    """final_point_binary_interaction_logits.py:83-135: per cloud the logits of all (pair, context, coalition) rows at
+    the normal pose, at the adversarial pose (<mode>_adv/transform_params.npy) and, for the region whose Shapley value
+    varies most (range_rank 01), at the normal pose with that region's pair list.  samples replaces the reference's
+    dataset loader; selected_sample_idx (default: all) its global of that name.  args.gen_pair_seed names the
+    interaction_seed<seed>/ folder written by final_gen_pair."""
+    import os
+    from .tools.final_util import load_model
+    if model is None:
+        model = load_model(args)
+    dev = _device_of(model)
+    with torch.no_grad():
+        for pc_idx, (data, lbl, name) in enumerate(samples):
+            if selected_sample_idx is not None and pc_idx not in selected_sample_idx:
+                continue
+            data = data.to(dev)
+            base_folder = args.exp_folder + "%s/" % name
+            interaction_folder = base_folder + "interaction_seed%d/" % args.gen_pair_seed
+            single_region_folder = interaction_folder + "%s_adv_single_region/" % args.mode
+            region_id = np.load(base_folder + "region_id.npy")
+            save_logits_all_orders(model, data, region_id, interaction_folder + "normal/", args)
+            transform_params = np.load(interaction_folder + "%s_adv/transform_params.npy" % args.mode).astype(np.float32)
+            data_disturb = disturb_fn(data, torch.from_numpy(transform_params).to(dev))
+            save_logits_all_orders(model, data_disturb, region_id, interaction_folder + "%s_adv/" % args.mode, args)
+            for region_folder_name in sorted(os.listdir(single_region_folder)):
+                if not os.path.isdir(single_region_folder + region_folder_name):
+                    continue
+                if int(region_folder_name[10:12]) != 1:          # range_rank<rr>_region<ii>: only the top-ranked region
+                    continue
+                save_logits_all_orders(model, data, region_id, single_region_folder + region_folder_name + "/normal/", args)

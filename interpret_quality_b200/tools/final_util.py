@@ -49,6 +49,11 @@ class IOStream():
         self.f.close()
 
 
+def cal_rank(values):
+    """0-based ascending rank of every entry (tools/final_util.py:103-106)."""
+    return np.argsort(np.argsort(values))
+
+
 def set_random(seed):
     """Seeds python hashing, numpy's legacy stream and torch exactly like the reference, so that
     replaying the same call sequence afterwards reproduces its permutations / pairs / contexts."""

@@ -195,7 +195,7 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables", "smoothness"):
+        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables", "smoothness", "interaction_pipeline"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -421,3 +421,61 @@ def smoothness():
 
 if __name__ == "__main__" and "smoothness" in sys.argv[1:]:
     smoothness()
+
+
+def interaction_pipeline():
+    """interaction_pipeline.npz: the reference's whole interaction chain on the synthetic cloud (PointNet, CPU, 12 rotation
+    poses): final_gen_pair.py save_pair_random :302 -> check_adv_success :221 -> save_pair_single_region :145 ->
+    save_context :45 -> save_pred_label :90, then final_point_binary_interaction_logits.save_logits :83 and
+    final_cal_interactions.cal_interaction :49 (gt and pred).  Every file the chain writes is stored under its path
+    relative to the experiment folder.  The dataset loaders (absent data) are replaced by a one-cloud list and
+    load_model by the synthetic-weight model; the functions themselves are the reference's, unmodified."""
+    import tempfile
+    import final_gen_pair as ref_gp
+    import final_rotate_center_enum_all as ref_r
+    from tools.final_util import set_random as ref_set_random
+    data, fps_idx, region_id = base_inputs(1024)
+    lbl = torch.tensor([LBL])
+    model, margs = load_ref_model("pointnet")
+    d = tempfile.mkdtemp() + "/"
+    base = d + "cloud0/"
+    os.makedirs(base + "rotate_all/")
+    np.save(base + "region_id.npy", region_id)
+    ga = types.SimpleNamespace(angle_threshold=np.pi / 4, num_grid_enum_rotate=6)
+    angles = ref_r.generate_rotate_angle(ga, torch.device("cpu")).numpy()[::18]          # 12 of the 216 poses
+    np.save(base + "rotate_all/angle_tuple.npy", angles)
+    np.save(base + "rotate_all/region_shapley_value.npy", np.random.RandomState(11).randn(angles.shape[0], R) * 0.1)
+    a = types.SimpleNamespace(num_points=1024, num_regions=R, model="pointnet", dataset="shapenet", mode="rotate", seed=1,
+                              gen_pair_seed=1, exp_folder=d, device=torch.device("cpu"), test_batch_size=1,
+                              ratio=[0.0, 0.1, 1.0], num_pairs_random=5, num_save_context_max=3, softmax_type="modified",
+                              interaction_batch_size=2, output_type="gt")
+    for mod in (ref_gp, ref_il, ref_ci):
+        mod.DataLoader = lambda *args_, **kw: [(data, lbl)]
+        mod.ShapeNetDataset_Shapley_test = lambda *args_, **kw: None
+        mod.load_model = lambda args_: model
+        mod.folder_name_list = ["cloud0"]
+        mod.selected_sample_idx = [0]
+    ref_set_random(a.seed)
+    ref_gp.save_pair_random(a)
+    ref_gp.check_adv_success(a, disturb_fn=ref_r.rotate_xyz)
+    ref_gp.save_pair_single_region(a)
+    ref_gp.save_context(a)
+    ref_gp.save_pred_label(a, disturb_fn=ref_r.rotate_xyz)
+    ref_il.save_logits(a, ref_r.rotate_xyz)
+    ref_ci.cal_interaction(a)
+    a.output_type = "pred"
+    ref_ci.cal_interaction(a)
+    out = {}
+    for root, _, files in os.walk(d):
+        for f in files:
+            rel = os.path.relpath(os.path.join(root, f), d)
+            if f.endswith(".npy"):
+                out[rel] = np.load(os.path.join(root, f))
+            elif f.endswith(".pt"):
+                out[rel] = torch.load(os.path.join(root, f)).numpy()
+    np.savez_compressed(os.path.join(HERE, "interaction_pipeline.npz"), **out)
+    print("interaction_pipeline.npz written:", len(out), "files")
+
+
+if __name__ == "__main__" and "interaction_pipeline" in sys.argv[1:]:
+    interaction_pipeline()
