@@ -90,3 +90,70 @@ def test_dgcnn_other_neighbourhood_sizes(k):
     want = nets.forward("dgcnn", torch.from_numpy(x).permute(0, 2, 1).contiguous(),
                         {kk: torch.from_numpy(np.asarray(v)) for kk, v in sd.items()}, k=k).numpy()
     assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max()
+
+
+GUARD = 1 << 20
+
+
+def guarded(nbytes):
+    """A uint8 buffer of nbytes between two 1 MiB bands of 0xA5; returns (whole, interior view)."""
+    nbytes = (int(nbytes) + 255) // 256 * 256
+    whole = torch.full((GUARD + nbytes + GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+    return whole, whole[GUARD:GUARD + nbytes]
+
+
+def intact(whole):
+    return bool((whole[:GUARD] == 0xA5).all()) and bool((whole[-GUARD:] == 0xA5).all())
+
+
+@pytest.mark.parametrize("name", ["dgcnn", "gcnn", "pointnet", "pointnet2", "pointconv"])
+def test_forward_stays_inside_workspace_logits_and_input(name):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds writes are looked for with guard bands:
+    the forward gets EXACTLY iq_model_workspace_bytes of scratch, its logits and its input between 0xA5 bands, for a
+    batch that is not a multiple of the internal chunk; bands must survive and the result must equal the normal call."""
+    from interpret_quality_b200 import _lib
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True, device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict(name))
+    model.set_chunk(8)
+    x = torch.from_numpy(masked_clouds()[:19]).to(DEV)                    # 19 clouds: chunks of 8, 8, 3
+    B, N = x.shape[0], x.shape[1]
+    want = model.forward_point_major(x)
+    lib = _lib.load()
+    h = model._get_handle()
+    need = lib.iq_model_workspace_bytes(h, B, N)
+    assert need > 0
+    ws_whole, ws = guarded(need)
+    out_whole, out = guarded(B * model.output_channels * 4)
+    in_whole, xin = guarded(x.numel() * 4)
+    xin[:x.numel() * 4].copy_(x.reshape(-1).view(torch.uint8))
+    with torch.cuda.device(DEV):
+        _lib.check(lib.iq_model_forward(h, xin.data_ptr(), 1, B, N, out.data_ptr(), ws.data_ptr(), int(need), 0, 0,
+                                        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert intact(ws_whole) and intact(out_whole) and intact(in_whole)
+    got = out[:B * model.output_channels * 4].view(torch.float32).reshape(B, model.output_channels)
+    assert torch.equal(got, want)
+    assert torch.equal(xin[:x.numel() * 4].view(torch.float32).reshape(x.shape), x)          # the input is read-only
+    with torch.cuda.device(DEV):                                            # one byte short must be refused, not overrun
+        rc = lib.iq_model_forward(h, xin.data_ptr(), 1, B, N, out.data_ptr(), ws.data_ptr(), int(need) - 4096, 0, 0,
+                                  torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and "workspace" in _lib.last_error()
+
+
+def test_coalition_kernels_stay_inside_their_outputs():
+    """mask_shapley writes exactly its ((R+1)*bs, N, 3) output: guard bands either side survive."""
+    from oracle import geom
+    data = synthetic.make_cloud(1024)
+    rid = geom.region_id(data[0], geom.fps(data, R)[0])
+    d = torch.from_numpy(data[0]).to(DEV)
+    center = torch.from_numpy(coalition.center_of(data)).to(DEV)      # the same fp32 centre on both sides
+    orders = ops.to_dev_i64(synthetic.make_orders(3, R), DEV)
+    region = ops.to_dev_i64(rid, DEV)
+    rows = 3 * (R + 1)
+    whole, buf = guarded(rows * 1024 * 3 * 4)
+    out = buf[:rows * 1024 * 3 * 4].view(torch.float32).reshape(rows, 1024, 3)
+    ops.mask_shapley(d, center, orders, region, out=out)
+    torch.cuda.synchronize()
+    assert intact(whole)
+    want = geom.mask_shapley(data[0], coalition.center_of(data), synthetic.make_orders(3, R), rid)
+    assert np.array_equal(out.cpu().numpy(), want)
