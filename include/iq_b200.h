@@ -113,6 +113,11 @@ void iq_model_destroy(iq_model *m);
 int iq_model_set_chunk(iq_model *m, int chunk);
 int iq_model_get_chunk(const iq_model *m);
 
+/* chunks in flight (1..4): chunks are dealt round-robin over the caller's stream and lanes-1 internal side streams that
+ * fork from and join back into it, each lane with its own slice of the workspace (iq_model_workspace_bytes accounts for
+ * it).  Default 2; results do not depend on it.  The environment variable IQ_LANES overrides it (diagnostics). */
+int iq_model_set_lanes(iq_model *m, int lanes);
+
 /* bytes of scratch iq_model_forward needs for B clouds of N points */
 int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N);
 

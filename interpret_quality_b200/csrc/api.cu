@@ -135,6 +135,13 @@ int iq_model_set_chunk(iq_model *m, int chunk)
 
 int iq_model_get_chunk(const iq_model *m) { return m ? m->impl->chunk : -1; }
 
+int iq_model_set_lanes(iq_model *m, int lanes)
+{
+    IQ_CHECK(m && lanes >= 1 && lanes <= Model::MAX_LANES, "iq_model_set_lanes: lanes must be 1..4");
+    m->impl->lanes = lanes;
+    return 0;
+}
+
 int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N)
 {
     if (!m) { set_error("iq_model_workspace_bytes: null model"); return -1; }

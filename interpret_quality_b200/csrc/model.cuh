@@ -51,11 +51,15 @@ struct DeviceArena {              // owns every device buffer of a model
 
 class Model {
 public:
-    virtual ~Model() {}
+    virtual ~Model();
     virtual const char *kind() const = 0;
     int num_classes = 10;
     // largest number of clouds one internal pass handles; forward() loops over chunks
     int chunk = 64;
+    // chunks in flight: 1 = the caller's stream only, n = dealt round-robin over it and n-1 internal side streams
+    // (own scratch per lane); the results do not depend on it
+    static constexpr int MAX_LANES = 4;
+    int lanes = 2;
     // GEMM engine for the large products: 1 = tcgen05 3xTF32 (default), 0 = exact fp32 SIMT
     int engine = 1;
     // bytes of workspace needed to run `B` clouds of `N` points (already capped by chunk)
@@ -64,6 +68,10 @@ public:
                 float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st);
 
     DeviceArena arena_;
+
+private:
+    cudaStream_t side_[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev_ = nullptr, join_ev_[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
 
 protected:
     // width of the pooled per-cloud feature the body hands to the head

@@ -1,5 +1,6 @@
 // Shared model plumbing: error state, device arena, BN folding, chunked forward.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -136,27 +137,67 @@ void split_tf32_host(const std::vector<float> &w, std::vector<float> &hi, std::v
     }
 }
 
+Model::~Model()
+{
+    for (int i = 0; i < MAX_LANES - 1; ++i) {
+        if (side_[i]) cudaStreamDestroy(side_[i]);
+        if (join_ev_[i]) cudaEventDestroy(join_ev_[i]);
+    }
+    if (fork_ev_) cudaEventDestroy(fork_ev_);
+}
+
 int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,
                 float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st)
 {
     float *pooled = ws.take<float>(B * pooled_dim());
-    const int64_t head_mark = ws.off;
-    int64_t peak = ws.off;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
-        const int64_t Bc = std::min<int64_t>(chunk, B - b0);
-        ws.off = head_mark;                                        // every chunk reuses the same scratch
-        const int rc = run_body(ws, ws.dry ? nullptr : x + b0 * N * 3, point_major, Bc, N,
-                                ws.dry ? nullptr : pooled + b0 * pooled_dim(),
-                                aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
-                                aux_crt ? aux_crt + b0 * 1024 : nullptr, st);
-        if (rc != 0) return rc;
-        peak = std::max(peak, ws.off);
-        if (ws.dry) break;                                         // the first chunk is the largest
+    const int64_t head_mark = round_up(ws.off, 256);
+    // scratch of one chunk, measured on the largest one
+    Workspace probe;
+    probe.dry = true;
+    probe.off = head_mark;
+    if (int rc = run_body(probe, nullptr, point_major, std::min<int64_t>(chunk, B), N, nullptr, nullptr, nullptr, st)) return rc;
+    const int64_t lane_bytes = round_up(probe.off, 256) - head_mark;
+    // Chunks are independent: with lanes > 1 they are dealt round-robin to the caller's stream and internal side
+    // streams, each lane with its own scratch, so one chunk's kernel tails and pipeline fill overlap another's
+    // steady state.
+    static const int lanes_env = getenv("IQ_LANES") ? atoi(getenv("IQ_LANES")) : 0;
+    const int want = std::min(std::max(lanes_env > 0 ? lanes_env : lanes, 1), (int)MAX_LANES);
+    const int nl = (int)std::min<int64_t>(want, ceil_div(B, chunk));
+    const int64_t body_end = head_mark + nl * lane_bytes;
+    if (!ws.dry) {
+        IQ_CHECK(body_end <= ws.size, "forward: workspace too small");
+        if (nl > 1) {
+            if (!fork_ev_) IQ_CUDA(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
+            IQ_CUDA(cudaEventRecord(fork_ev_, st));                 // the side lanes see everything queued so far
+            for (int l = 0; l < nl - 1; ++l) {
+                if (!side_[l]) {
+                    IQ_CUDA(cudaStreamCreateWithFlags(&side_[l], cudaStreamNonBlocking));
+                    IQ_CUDA(cudaEventCreateWithFlags(&join_ev_[l], cudaEventDisableTiming));
+                }
+                IQ_CUDA(cudaStreamWaitEvent(side_[l], fork_ev_, 0));
+            }
+        }
+        int64_t i = 0;
+        for (int64_t b0 = 0; b0 < B; b0 += chunk, ++i) {
+            const int64_t Bc = std::min<int64_t>(chunk, B - b0);
+            const int lane = (int)(i % nl);
+            Workspace lw = ws;
+            lw.off = head_mark + lane * lane_bytes;
+            lw.size = head_mark + (lane + 1) * lane_bytes;
+            const int rc = run_body(lw, x + b0 * N * 3, point_major, Bc, N, pooled + b0 * pooled_dim(),
+                                    aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
+                                    aux_crt ? aux_crt + b0 * 1024 : nullptr, lane == 0 ? st : side_[lane - 1]);
+            if (rc != 0) return rc;
+        }
+        for (int l = 0; l < nl - 1; ++l) {                            // the head (and the caller) wait for every lane
+            IQ_CUDA(cudaEventRecord(join_ev_[l], side_[l]));
+            IQ_CUDA(cudaStreamWaitEvent(st, join_ev_[l], 0));
+        }
     }
     ws.off = head_mark;
     const int rc = run_head(ws, pooled, B, logits, st);
     if (rc != 0) return rc;
-    ws.off = std::max(peak, ws.off);
+    ws.off = std::max(body_end, ws.off);
     return 0;
 }
 

@@ -112,6 +112,12 @@ class IQModule(nn.Module):
         _lib.check(_lib.load().iq_model_set_chunk(self._get_handle(), int(chunk)))
         self._ws = None
 
+    def set_lanes(self, lanes):
+        """Chunks in flight, 1..4 (tuning knob; results do not depend on it): chunks alternate between the caller's
+        stream and internal side streams so that one chunk's kernel tails overlap the next chunk's work."""
+        _lib.check(_lib.load().iq_model_set_lanes(self._get_handle(), int(lanes)))
+        self._ws = None
+
     def _workspace(self, B, N, device):
         lib = _lib.load()
         need = lib.iq_model_workspace_bytes(self._get_handle(), B, N)

@@ -157,3 +157,28 @@ def test_coalition_kernels_stay_inside_their_outputs():
     assert intact(whole)
     want = geom.mask_shapley(data[0], coalition.center_of(data), synthetic.make_orders(3, R), rid)
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("name", ["dgcnn", "pointnet2"])
+def test_lanes_do_not_change_the_result(name):
+    """Chunks in flight (iq_model_set_lanes) is scheduling only: 1, 2, 3 and 4 lanes give bit-identical logits, also
+    when the caller's stream is not the default one and has work queued before and after the forward."""
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True, device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict(name))
+    model.set_chunk(4)
+    x = torch.from_numpy(masked_clouds()[:23]).to(DEV)                    # 6 chunks, the last one ragged
+    model.set_lanes(1)
+    want = model.forward_point_major(x).clone()
+    side = torch.cuda.Stream(device=DEV)
+    for lanes in (2, 3, 4):
+        model.set_lanes(lanes)
+        assert torch.equal(model.forward_point_major(x), want)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            xs = x * 1.0                                                    # produced on the caller's stream just before
+            got = model.forward_point_major(xs)
+            total = got.sum()                                               # consumed on it right after
+        side.synchronize()
+        assert torch.equal(got, want) and torch.isfinite(total)
+    with pytest.raises(Exception):
+        model.set_lanes(5)
