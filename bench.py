@@ -63,7 +63,9 @@ def config_of(a, n_gpus):
             "num_points": a.points, "num_regions": R, "permutations_per_step_per_gpu": a.perms,
             "forwards_per_step_per_gpu": a.perms * (R + 1), "parallelism": "perm-shard x%d" % n_gpus,
             "l2_policy": "256 MiB buffer rewritten between timed steps (flush); per-step working set also exceeds L2",
-            "weights": "seeded trained-like random init (interpret_quality_b200/synthetic.py)"}
+            "weights": "seeded trained-like random init (interpret_quality_b200/synthetic.py)",
+            "chunk_lanes": "library default (2 chunks in flight, PointNet 3); the per-kernel roofline pass runs 1 lane so "
+                           "that every kernel is timed alone"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -340,10 +342,14 @@ def run_b200(a):
     # per-kernel timing of one more step (CUDA events around every launch, on the launching stream)
     roofline, breakdown = None, None
     if rank == 0:
+        lanes = model.get_lanes()
+        model.set_lanes(1)                                   # one chunk at a time: every kernel is timed alone on its stream
+        local_step()                                         # (re-sizes the workspace outside the profiled step)
         _lib.profile_enable(True)
         local_step()                                         # rank-local: no collective outside the timed region
         rep = _lib.profile_report()
         _lib.profile_enable(False)
+        model.set_lanes(lanes)
         pk = peaks()
         work = kernel_work(a)
         tot = sum(ms for ms, _ in rep.values())

@@ -117,6 +117,7 @@ int iq_model_get_chunk(const iq_model *m);
  * fork from and join back into it, each lane with its own slice of the workspace (iq_model_workspace_bytes accounts for
  * it).  Default 2; results do not depend on it.  The environment variable IQ_LANES overrides it (diagnostics). */
 int iq_model_set_lanes(iq_model *m, int lanes);
+int iq_model_get_lanes(const iq_model *m);
 
 /* bytes of scratch iq_model_forward needs for B clouds of N points */
 int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "iq_model_destroy": (None, [_vp]),
     "iq_model_set_chunk": (_int, [_vp, _int]),
     "iq_model_set_lanes": (_int, [_vp, _int]),
+    "iq_model_get_lanes": (_int, [_vp]),
     "iq_model_get_chunk": (_int, [_vp]),
     "iq_model_workspace_bytes": (_i64, [_vp, _i64, _i64]),
     "iq_model_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -142,6 +142,8 @@ int iq_model_set_lanes(iq_model *m, int lanes)
     return 0;
 }
 
+int iq_model_get_lanes(const iq_model *m) { return m ? m->impl->lanes : -1; }
+
 int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N)
 {
     if (!m) { set_error("iq_model_workspace_bytes: null model"); return -1; }

@@ -118,6 +118,9 @@ class IQModule(nn.Module):
         _lib.check(_lib.load().iq_model_set_lanes(self._get_handle(), int(lanes)))
         self._ws = None
 
+    def get_lanes(self):
+        return int(_lib.load().iq_model_get_lanes(self._get_handle()))
+
     def _workspace(self, B, N, device):
         lib = _lib.load()
         need = lib.iq_model_workspace_bytes(self._get_handle(), B, N)
