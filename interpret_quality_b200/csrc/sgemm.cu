@@ -152,18 +152,32 @@ sgemm_kernel(const GemmDesc g)
 
     if (g.C_hi) {
         float *Ch = g.C_hi + (int64_t)bz * g.strideC, *Cl = g.C_lo + (int64_t)bz * g.strideC;
+        const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ch) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(Cl) & 15) == 0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
             if (m >= g.M) continue;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-                if (n >= g.N) continue;
-                const float h = __uint_as_float((__float_as_uint(acc[i][j]) + 0x1000u) & 0xffffe000u);
-                const float l = acc[i][j] - h;
-                Ch[(int64_t)m * g.ldc + n] = h;
-                Cl[(int64_t)m * g.ldc + n] = __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+            for (int hh = 0; hh < 2; ++hh) {
+                const int n = n0 + hh * 64 + tx * 4;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float v = acc[i][hh * 4 + j];
+                    hi[j] = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+                    const float l = v - hi[j];
+                    lo[j] = __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+                }
+                float *dh = Ch + (int64_t)m * g.ldc + n, *dl = Cl + (int64_t)m * g.ldc + n;
+                if (vec_ok && n + 3 < g.N) {
+                    *reinterpret_cast<float4 *>(dh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4 *>(dl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < g.N) { dh[j] = hi[j]; dl[j] = lo[j]; }
+                }
             }
         }
     }
