@@ -363,11 +363,7 @@ def smoothness():
     (:245-268).  torch.symeig (:41) no longer exists in this torch; it is provided here as a thin forwarder to
     torch.linalg.eigh (same ascending eigenvalue order, eigenvectors in columns), the reference file is unmodified."""
     import tempfile
-    if not hasattr(torch, "symeig") or True:
-        torch.symeig = lambda A, eigenvectors=True: torch.linalg.eigh(A)
-    sys.modules.setdefault("final_data_shapley", types.ModuleType("final_data_shapley"))
-    for nm in ("ModelNet_Loader_Shapley_test", "ShapeNetDataset_Shapley_test"):
-        setattr(sys.modules["final_data_shapley"], nm, getattr(sys.modules["final_data_shapley"], nm, None))
+    torch.symeig = lambda A, eigenvectors=True: torch.linalg.eigh(A)
     import final_smoothness_center_enum_all as ref_sm
     import time
     data, fps_idx, region_id = base_inputs(1024)
