@@ -34,6 +34,10 @@ const char *iq_last_error(void);
 /* number of CUDA kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t iq_launch_count(void);
 
+/* The diagnostic environment switches (IQ_LANES, IQ_TC_DBG, IQ_KNN_DBG, IQ_TC_NO_ATM, IQ_TC_NO_GATHER, IQ_NO_COLLAPSE)
+ * are read once per process; this makes the next launch read them again (scripts/*_probe.py flip them in-process). */
+int iq_debug_reload_env(void);
+
 /* Per-kernel timing for bench.py's roofline leg: while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  iq_profile_report synchronises the device and returns the
  * number of distinct kernel names, filling up to `cap` (name, total milliseconds, launches) triples. */
@@ -79,6 +83,14 @@ int iq_mask_shapley(const float *data_dev, const float *center_dev, const int64_
 int iq_mask_interaction(const float *data_dev, const float *center_dev, const int64_t *contexts_dev, int64_t ctx,
                         int64_t m, int64_t region_i, int64_t region_j, const int64_t *region_id_dev, int64_t R,
                         int64_t N, int point_major, float *out_dev, void *stream);
+
+/* The same block for ALL pairs of compute_order_interaction_logits at once (the reference loops over them on the host,
+ * final_point_binary_interaction_logits.py:37-41): pairs (P,2) i64, contexts (P,ctx,m) i64 ->
+ * out (P*ctx*4, 3, N) or (P*ctx*4, N, 3); cloud (p*ctx + k)*4 + v is variant v of context k of pair p. */
+int iq_mask_interaction_pairs(const float *data_dev, const float *center_dev, const int64_t *pairs_dev,
+                              const int64_t *contexts_dev, int64_t P, int64_t ctx, int64_t m,
+                              const int64_t *region_id_dev, int64_t R, int64_t N, int point_major, float *out_dev,
+                              void *stream);
 
 /* ---- reward and reductions ----------------------------------------------------------- */
 
@@ -129,6 +141,25 @@ int64_t iq_model_workspace_bytes(iq_model *m, int64_t B, int64_t N);
 int iq_model_forward(iq_model *m, const float *x_dev, int point_major, int64_t B, int64_t N, float *logits_dev,
                      void *workspace_dev, int64_t workspace_bytes, float *trans_feat_dev, int64_t *crt_points_dev,
                      void *stream);
+
+/* The same forward for a batch of COALITION clouds: clouds produced by the reference's masking rule
+ * (tools/final_common.py:56-60 mask_data_batch, final_shapley_value.py:74-88 mask_data,
+ * final_point_binary_interaction_logits.py:42-56), i.e. every point of an absent region sits on masked_to_dev
+ * (3 floats on the device: `center`, tools/final_common.py:80).  Coincident points have identical rows in every
+ * layer, so DGCNN / GCNN / PointNet evaluate each cloud on its kept points plus a few copies of that location
+ * (grouped by compacted size in steps of 128 points) -- the logits are those of iq_model_forward up to the
+ * summation order of the average pool.  PointNet++ / PointConv (FPS, ball query and density depend on the
+ * multiplicities) and clouds without coincident points run exactly as in iq_model_forward.  One host round trip
+ * (per-cloud kept counts) inside the call; the stream is synchronised once. */
+int iq_model_forward_coalitions(iq_model *m, const float *x_dev, int point_major, int64_t B, int64_t N,
+                                const float *masked_to_dev, float *logits_dev, void *workspace_dev,
+                                int64_t workspace_bytes, void *stream);
+/* rows evaluated / (B*N) of the last iq_model_forward_coalitions call of this model (1 when nothing collapsed) */
+double iq_model_last_row_fraction(const iq_model *m);
+/* how the last forward of this model was evaluated: counts[t-1] = clouds run at 128*t points (a plain forward has all
+ * its clouds in the last entry).  Fills up to `cap` entries, returns the number of entries (ceil(N/128)); bench.py
+ * derives the work each kernel really did from it. */
+int iq_model_last_buckets(const iq_model *m, int64_t *counts, int cap);
 
 /* ---- building blocks of the forward pass, exported for unit tests ---------------------------- */
 

@@ -17,6 +17,7 @@ SIGNATURES = {
     "iq_version": (_int, []),
     "iq_last_error": (ctypes.c_char_p, []),
     "iq_launch_count": (ctypes.c_uint64, []),
+    "iq_debug_reload_env": (_int, []),
     "iq_profile_enable": (_int, [_int]),
     "iq_profile_report": (_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_longlong), _int]),
@@ -26,6 +27,7 @@ SIGNATURES = {
     "iq_center": (_int, [_vp, _i64, _vp, _vp]),
     "iq_mask_shapley": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "iq_mask_interaction": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp]),
+    "iq_mask_interaction_pairs": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp]),
     "iq_reward": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp]),
     "iq_shapley_accumulate": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "iq_interaction_reduce": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, _vp]),
@@ -38,6 +40,9 @@ SIGNATURES = {
     "iq_model_get_chunk": (_int, [_vp]),
     "iq_model_workspace_bytes": (_i64, [_vp, _i64, _i64]),
     "iq_model_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "iq_model_forward_coalitions": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "iq_model_last_row_fraction": (ctypes.c_double, [_vp]),
+    "iq_model_last_buckets": (_int, [_vp, ctypes.POINTER(_i64), _int]),
     "iq_ball_query": (_int, [_vp, _vp, _i64, _i64, _i64, ctypes.c_double, _int, _vp, _vp]),
     "iq_knn_xyz": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "iq_knn_features": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]),

@@ -16,6 +16,12 @@ int iq_version(void) { return 100; }
 const char *iq_last_error(void) { return last_error(); }
 uint64_t iq_launch_count(void) { return g_launch_count; }
 
+int iq_debug_reload_env(void)
+{
+    env_forget();
+    return 0;
+}
+
 int iq_profile_enable(int on)
 {
     profile_enable(on != 0);
@@ -67,6 +73,17 @@ int iq_mask_interaction(const float *data, const float *center, const int64_t *c
     IQ_CHECK(contexts || m == 0 || ctx == 0, "iq_mask_interaction: null contexts");
     return launch_mask_interaction(data, center, contexts, ctx, m, region_i, region_j, region_id, R, N, point_major, out,
                                    as_stream(stream));
+}
+
+int iq_mask_interaction_pairs(const float *data, const float *center, const int64_t *pairs, const int64_t *contexts,
+                              int64_t P, int64_t ctx, int64_t m, const int64_t *region_id, int64_t R, int64_t N,
+                              int point_major, float *out, void *stream)
+{
+    IQ_CHECK(data && center && region_id && out, "iq_mask_interaction_pairs: null pointer");
+    IQ_CHECK(pairs || P == 0, "iq_mask_interaction_pairs: null pairs");
+    IQ_CHECK(contexts || m == 0 || ctx == 0 || P == 0, "iq_mask_interaction_pairs: null contexts");
+    return launch_mask_interaction_pairs(data, center, pairs, contexts, P, ctx, m, region_id, R, N, point_major, out,
+                                         as_stream(stream));
 }
 
 int iq_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v, void *stream)
@@ -154,7 +171,24 @@ int iq_model_forward(iq_model *m, const float *x, int point_major, int64_t B, in
                      int64_t ws_bytes, float *trans_feat, int64_t *crt_points, void *stream)
 {
     IQ_CHECK(m, "iq_model_forward: null model");
-    return m->impl->forward(x, point_major, B, N, logits, ws, ws_bytes, trans_feat, crt_points, as_stream(stream));
+    return m->impl->forward(x, point_major, B, N, logits, ws, ws_bytes, trans_feat, crt_points, nullptr, as_stream(stream));
+}
+
+int iq_model_forward_coalitions(iq_model *m, const float *x, int point_major, int64_t B, int64_t N, const float *masked_to,
+                                float *logits, void *ws, int64_t ws_bytes, void *stream)
+{
+    IQ_CHECK(m, "iq_model_forward_coalitions: null model");
+    return m->impl->forward(x, point_major, B, N, logits, ws, ws_bytes, nullptr, nullptr, masked_to, as_stream(stream));
+}
+
+double iq_model_last_row_fraction(const iq_model *m) { return m ? m->impl->last_row_fraction : -1.0; }
+
+int iq_model_last_buckets(const iq_model *m, int64_t *counts, int cap)
+{
+    IQ_CHECK(m && (counts || cap == 0), "iq_model_last_buckets: null argument");
+    const int n = (int)m->impl->last_buckets.size();
+    for (int i = 0; i < n && i < cap; ++i) counts[i] = m->impl->last_buckets[i];
+    return n;
 }
 
 int iq_ball_query(const float *xyz, const float *new_xyz, int64_t B, int64_t N, int64_t S, double radius, int nsample,

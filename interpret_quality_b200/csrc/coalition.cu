@@ -109,13 +109,21 @@ int launch_mask_shapley(const float *data, const float *center, const int64_t *o
 // so that -0.0 inputs come out exactly as they do there.  Output is
 // channel-first (4*ctx, 3, N) like the reference, or point-major (4*ctx, N, 3)
 // when the caller feeds the forward pass directly.
+// With `pairs` ((P,2) on the device) the launch covers every pair at once: context k belongs to pair k / ctx_per_pair
+// (the reference loops over the pairs on the host, final_point_binary_interaction_logits.py:37).
 __global__ void __launch_bounds__(256)
 mask_interaction_kernel(const float *__restrict__ data, const float *__restrict__ center,
                         const int64_t *__restrict__ contexts, int m, int region_i, int region_j,
+                        const int64_t *__restrict__ pairs, int ctx_per_pair,
                         const int64_t *__restrict__ region_id, int R, int N, int point_major, float *__restrict__ out)
 {
     __shared__ unsigned char inS[256];
     const int k = blockIdx.x;
+    if (pairs) {
+        const int64_t p = k / ctx_per_pair;
+        region_i = (int)pairs[2 * p];
+        region_j = (int)pairs[2 * p + 1];
+    }
     for (int r = threadIdx.x; r < 256; r += blockDim.x) inS[r] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < m; t += blockDim.x) {
@@ -152,7 +160,22 @@ int launch_mask_interaction(const float *data, const float *center, const int64_
     IQ_CHECK(R >= 1 && R <= 255, "mask_interaction: num_regions must be in [1,255]");
     if (ctx == 0) return 0;
     mask_interaction_kernel<<<(unsigned)ctx, 256, 0, st>>>(data, center, contexts, (int)m, (int)region_i, (int)region_j,
-                                                          region_id, (int)R, (int)N, point_major, out);
+                                                          nullptr, 1, region_id, (int)R, (int)N, point_major, out);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_mask_interaction_pairs(const float *data, const float *center, const int64_t *pairs, const int64_t *contexts,
+                                  int64_t P, int64_t ctx, int64_t m, const int64_t *region_id, int64_t R, int64_t N,
+                                  int point_major, float *out, cudaStream_t st)
+{
+    ProfileScope _ps("mask_interaction", st);
+    IQ_CHECK(R >= 1 && R <= 255, "mask_interaction: num_regions must be in [1,255]");
+    IQ_CHECK(P * ctx < ((int64_t)1 << 31), "mask_interaction: too many contexts for one launch");
+    if (P * ctx == 0) return 0;
+    mask_interaction_kernel<<<(unsigned)(P * ctx), 256, 0, st>>>(data, center, contexts, (int)m, 0, 0, pairs, (int)ctx,
+                                                                region_id, (int)R, (int)N, point_major, out);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -220,11 +243,8 @@ int launch_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int so
     IQ_CHECK(C >= 2 && C <= 256 && lbl >= 0 && lbl < C, "reward: label out of range");
     if (B == 0) return 0;
     const size_t smem = sizeof(float) * 128 * (size_t)(C | 1);
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        IQ_CUDA(cudaFuncSetAttribute(reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024)
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&reward_kernel), (int)smem)) return rc;
     reward_kernel<<<(unsigned)ceil_div(B, 128), 128, smem, st>>>(logits, B, (int)C, (int)lbl, softmax_normal, v);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
@@ -303,11 +323,8 @@ int launch_interaction_reduce(const float *logits, int64_t P, int64_t ctx, int64
     if (total == 0) return 0;
     const int threads = C <= 64 ? 128 : 32;
     const size_t smem = sizeof(float) * threads * (size_t)((4 * C) | 1);
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        IQ_CUDA(cudaFuncSetAttribute(interaction_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024)
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&interaction_reduce_kernel), (int)smem)) return rc;
     interaction_reduce_kernel<<<(unsigned)ceil_div(total, threads), threads, smem, st>>>(logits, total, (int)C, (int)lbl,
                                                                                         softmax_normal, out);
     IQ_COUNT_LAUNCH();

@@ -32,6 +32,13 @@ const char *last_error();
 
 #define IQ_LAUNCH_CHECK() IQ_CUDA(cudaGetLastError())
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: cached per (kernel, current device), so a
+// process that drives several GPUs opts every one of them in.  Thread-safe.  Returns 0 or -2 (error recorded).
+int ensure_dynamic_smem(const void *func, int bytes);
+// environment switches of the diagnostics scripts, read once per process
+int env_int(const char *name, int fallback);
+void env_forget();                 // the next env_int() reads the environment again (iq_debug_reload_env)
+
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -35,6 +35,9 @@ public:
 
 protected:
     int pooled_dim() const override { return 2048; }
+    // A k-nearest-neighbour list sees at most k of the coincident copies (collapse.cu); the average pool carries the
+    // rest as a weight, which only the tcgen05 pooling epilogue implements.
+    int collapse_copies() const override { return engine == 1 ? k : -1; }
 
     int run_head(Workspace &ws, const float *g, int64_t B, float *logits, cudaStream_t st) override
     {
@@ -111,7 +114,7 @@ protected:
                 if (int rc = launch_sgemm(d, st)) return rc;
                 if (int rc = launch_topk_rows(dist, rows, N, N, k, 1, idx, st)) return rc;
             }
-            static const bool tc_all = getenv("IQ_TC_ALL") != nullptr;   // experiment: EdgeConv 2-3 P|Q on tcgen05 too
+            const bool tc_all = env_int("IQ_TC_ALL", 0) != 0;            // experiment: EdgeConv 2-3 P|Q on tcgen05 too
             if (l > 0 && tc && (!dynamic || l == 3 || tc_all)) {
                 TcGemm p;
                 p.A_hi = feat_hi + layers[l - 1].col; p.A_lo = feat_lo + layers[l - 1].col; p.lda = 512;
@@ -139,6 +142,7 @@ protected:
             c5.B_hi = feat_hi; c5.B_lo = feat_lo; c5.ldb = 512; c5.K = 512;
             c5.clouds = (int)Bc; c5.points = (int)N; c5.cout = 1024;
             c5.out_max = g; c5.out_mean = g + 1024; c5.ld_out = 2048; c5.bias = conv5.b; c5.act = ACT_LRELU;
+            c5.pool_extra = cur_.pool_extra;
             c5.tag = "tc_conv5_pool";
             return launch_gemm_tc(c5, st);
         }

@@ -43,9 +43,14 @@ constexpr int GA_THREADS = 384;          // gathered-A variant: three groups of 
 // 15.6 ms), so the POOL-only and the gather-only fields share storage and the STORE outputs are flags (they leave via TMA).
 struct TcParams {
     int K;                       // multiple of 4 (TMA zero-fills up to the next multiple of 32)
-    // STORE: units = (M/128) * (Ncols/BN), one accumulator tile each
-    int n_tiles;                 // Ncols / BN
-    int rows_per_batch;          // > 0: B rows live in the same batch as the A rows (Gram), else B is shared
+    union {
+        struct {
+            // STORE: units = (M/128) * (Ncols/BN), one accumulator tile each
+            int n_tiles;             // Ncols / BN
+            int rows_per_batch;      // > 0: B rows live in the same batch as the A rows (Gram), else B is shared
+        };
+        const float *pool_extra;     // POOL_RUN: weight of each group's last column beyond 1 (collapse.cu), or null
+    };
     int num_units, tiles_per_unit;
     int act;
     int out_c, out_hilo;         // STORE outputs present: fp32 and / or its tf32 hi/lo split
@@ -334,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             if (lane == 0) mbar_arrive(a_full);
         }
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-            float run_max = -INFINITY, run_sum = 0.0f;
+            float run_max = -INFINITY, run_sum = 0.0f, y_last = 0.0f;
             int run_arg = 0;
             for (int j = 0; j < p.tiles_per_unit; ++j) {
                 int a_row0, b_row0;
@@ -379,12 +384,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         float v[32];
                         tmem_ld32(taddr + c0, v);
                         if (POOL_RUN) {
+                            // the sum is taken per block of 32 columns first: the rounding error of a cloud's mean grows
+                            // with sqrt(32) + sqrt(blocks) instead of sqrt(points), so the collapsed and the plain
+                            // evaluation of a coalition cloud (different numbers of columns) agree to ~1e-6
+                            float blk = 0.0f;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const float y = apply_act(fmaf(p.alpha, v[i], b), p.act);
                                 if (y > run_max) { run_max = y; run_arg = j * BN + c0 + i; }
-                                run_sum += y;
+                                blk += y;
+                                if (i == 31) y_last = y;
                             }
+                            run_sum += blk;
                         } else {                                            // several groups inside this tile
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
@@ -409,7 +420,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 const int ch = mt * TBM + row_in_tile;
                 if (ch < p.cout) {
                     p.out_max[(int64_t)grp * p.ld_out + ch] = run_max;
-                    if (p.out_mean) p.out_mean[(int64_t)grp * p.ld_out + ch] = run_sum / (float)p.points;
+                    if (p.out_mean) {
+                        // the last column of a collapsed cloud stands for 1 + extra coincident points
+                        const float extra = p.pool_extra ? __ldg(p.pool_extra + grp) : 0.0f;
+                        p.out_mean[(int64_t)grp * p.ld_out + ch] = fmaf(extra, y_last, run_sum) / ((float)p.points + extra);
+                    }
                     if (p.out_arg) p.out_arg[(int64_t)grp * p.cout + ch] = run_arg;
                 }
             }
@@ -499,11 +514,7 @@ static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_
             if (int rc = make_map(&mclo, g.C_lo, g.M, g.N, g.ldc, 32)) return rc;
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        IQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gemm_tc_kernel<BN, STAGES, VAR>), S::TOTAL)) return rc;
     int grid = std::min(p.num_units, sm_count());
     if (ATM) {                                                  // a CTA keeps one row tile of A: grid = multiple of m_tiles
         grid = std::max(p.m_tiles, grid / p.m_tiles * p.m_tiles);
@@ -521,8 +532,7 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
     IQ_CHECK(tc_gemm_supported(g), "gemm_tc: unsupported shape");
     TcParams p = {};
     p.K = g.K; p.alpha = g.alpha; p.bias = g.bias; p.act = g.act; p.four_terms = g.four_terms;
-    const char *dbg = getenv("IQ_TC_DBG");
-    p.dbg = dbg ? atoi(dbg) : 0;
+    p.dbg = env_int("IQ_TC_DBG", 0);
     int64_t a_rows, b_rows;
     int bn;
     if (g.mode == 0) {
@@ -539,6 +549,8 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
         if (g.points >= bn) { p.num_units = g.clouds * p.m_tiles; p.tiles_per_unit = g.points / bn; }
         else { p.num_units = (int)(b_rows / bn) * p.m_tiles; p.tiles_per_unit = 1; }
         p.out_max = g.out_max; p.out_mean = g.out_mean; p.out_arg = g.out_arg; p.ld_out = g.ld_out;
+        p.pool_extra = g.pool_extra;
+        IQ_CHECK(!g.pool_extra || g.points >= bn, "gemm_tc: pool_extra needs groups of >= 128 columns");
         a_rows = g.cout;
         IQ_CHECK(g.out_max, "gemm_tc: pooling output missing");
         IQ_CHECK(g.points >= bn || (!g.out_mean && !g.out_arg), "gemm_tc: mean / argmax need groups of >= 128 columns");
@@ -556,7 +568,7 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
         default: return launch_tc_variant<32, 4, VAR_STORE_GATHER>(g, p, a_rows, b_rows, st);
         }
     }
-    if (g.mode == 1 && g.K <= 128 && g.lda % 4 == 0 && p.m_tiles <= sm_count() && !getenv("IQ_TC_NO_ATM"))
+    if (g.mode == 1 && g.K <= 128 && g.lda % 4 == 0 && p.m_tiles <= sm_count() && !env_int("IQ_TC_NO_ATM", 0))
         return g.points >= bn ? launch_tc_variant<128, 6, VAR_POOL_RUN_ATM>(g, p, a_rows, b_rows, st)
                               : launch_tc_variant<128, 6, VAR_POOL_TILE_ATM>(g, p, a_rows, b_rows, st);
     if (g.mode == 1)

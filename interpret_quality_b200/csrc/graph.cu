@@ -590,11 +590,7 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
     if (smem <= 200 * 1024 && N % 128 == 0 && B * (Cout / 32) * 8 < ((int64_t)1 << 31)) {
         {
             ProfileScope _ps("gather_max", st);
-            static bool attr_set = false;
-            if (!attr_set) {
-                IQ_CUDA(cudaFuncSetAttribute(gather_max_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_set = true;
-            }
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gather_max_smem_kernel), 200 * 1024)) return rc;
             const int64_t base_units = B * (Cout / 32);
             int psplit = 1;
             while (psplit < 4 && base_units * psplit < 120) psplit *= 2;   // fill the SMs, but keep the units fat

@@ -10,11 +10,21 @@ int launch_mask_shapley(const float *data, const float *center, const int64_t *o
 int launch_mask_interaction(const float *data, const float *center, const int64_t *contexts, int64_t ctx, int64_t m,
                             int64_t region_i, int64_t region_j, const int64_t *region_id, int64_t R, int64_t N,
                             int point_major, float *out, cudaStream_t st);
+int launch_mask_interaction_pairs(const float *data, const float *center, const int64_t *pairs, const int64_t *contexts,
+                                  int64_t P, int64_t ctx, int64_t m, const int64_t *region_id, int64_t R, int64_t N,
+                                  int point_major, float *out, cudaStream_t st);
 int launch_reward(const float *logits, int64_t B, int64_t C, int64_t lbl, int softmax_normal, float *v, cudaStream_t st);
 int launch_shapley_accumulate(const float *v, const int64_t *orders, int64_t bs, int64_t R, double *phi_sum,
                               cudaStream_t st);
 int launch_interaction_reduce(const float *logits, int64_t P, int64_t ctx, int64_t C, int64_t lbl, int softmax_normal,
                               double *out, cudaStream_t st);
+
+// collapse.cu -- coalition collapse: coincident masked points -> compacted clouds (see the file header)
+int launch_collapse_count(const float *x, int point_major, int64_t B, int64_t N, const float *loc, int32_t *kept,
+                          cudaStream_t st);
+int launch_collapse_compact(const float *x, int point_major, int64_t B, int64_t N, const float *loc, const int32_t *src,
+                            const int32_t *row_off, const int32_t *size, float *out, cudaStream_t st);
+int launch_scatter_rows(const float *in, const int32_t *dst, int64_t rows, int C, float *out, cudaStream_t st);
 
 // geometry.cu
 int launch_fps(const float *xyz, int64_t B, int64_t N, int64_t npoint, int64_t *idx64, int32_t *idx32, float *new_xyz,
@@ -70,6 +80,9 @@ struct TcGemm {
     float *out_max = nullptr, *out_mean = nullptr;
     int64_t *out_arg = nullptr;
     int64_t ld_out = 0;
+    // POOL, optional: per cloud, the LAST column stands for 1 + pool_extra[cloud] identical points (collapse.cu):
+    // mean = (sum + extra * y_last) / (points + extra); the max is unaffected
+    const float *pool_extra = nullptr;
     float alpha = 1.0f;
     const float *bias = nullptr;  // STORE: per output column; POOL: per output channel
     int act = ACT_NONE;

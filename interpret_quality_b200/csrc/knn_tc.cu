@@ -672,12 +672,7 @@ int launch_variant(const float *x_hi, const float *x_lo, int64_t ld, int64_t row
     CUtensorMap mbhi, mblo;
     if (int rc = make_map(&mbhi, x_hi, rows, p.K, ld, BN)) return rc;
     if (int rc = make_map(&mblo, x_lo, rows, p.K, ld, BN)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IQ_CUDA(cudaFuncSetAttribute(gram_knn_kernel<BN, STAGES, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     S::TOTAL));
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gram_knn_kernel<BN, STAGES, KMAX>), S::TOTAL)) return rc;
     const int grid = std::min(p.num_units, sm_count());
     gram_knn_kernel<BN, STAGES, KMAX><<<grid, KNN_THREADS, S::TOTAL, st>>>(mbhi, mblo, p);
     IQ_COUNT_LAUNCH();
@@ -704,8 +699,7 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
     KnnParams p;
     p.K = C; p.points = (int)N; p.m_tiles = (int)(N / TBM); p.num_units = (int)(clouds * p.m_tiles);
     p.nxx = nxx; p.nxx_parts = nxx_parts; p.masks = masks; p.x_hi = x_hi; p.x_lo = x_lo; p.ld = ld;
-    const char *dbg = getenv("IQ_KNN_DBG");
-    p.dbg = dbg ? atoi(dbg) : 0;
+    p.dbg = env_int("IQ_KNN_DBG", 0);
     {
         ProfileScope _ps(C <= 64 ? "tc_gram_knn_c64" : "tc_gram_knn_c128", st);
         int rc = C == 64 ? launch_variant<128, 5, 64>(x_hi, x_lo, ld, rows, p, st)

@@ -64,16 +64,39 @@ public:
     int engine = 1;
     // bytes of workspace needed to run `B` clouds of `N` points (already capped by chunk)
     int64_t workspace_bytes(int64_t B, int64_t N);
+    // collapse_loc (optional, device, 3 floats): the location the coalition masks moved the absent regions to; clouds
+    // are then evaluated on their kept points + a few copies of it (collapse.cu) -- same logits, fewer rows
     int forward(const float *x, int layout_point_major, int64_t B, int64_t N, float *logits, void *ws, int64_t ws_bytes,
-                float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st);
+                float *aux_trans_feat, int64_t *aux_crt, const float *collapse_loc, cudaStream_t st);
+    // statistics of the last collapsed forward: rows evaluated / rows of the uncollapsed batch (1 when not collapsed)
+    double last_row_fraction = 1.0;
+    // clouds of the last forward per evaluated size: last_buckets[t-1] = clouds run at 128*t points (plain: all at N)
+    std::vector<int64_t> last_buckets;
 
     DeviceArena arena_;
 
 private:
     cudaStream_t side_[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev_ = nullptr, join_ev_[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+    int32_t *host_meta_ = nullptr;     // pinned staging of the collapse plan (kept counts in, sorted order out)
+    int64_t host_meta_cap_ = 0;
+    int plan_collapsed(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,
+                       const float *collapse_loc, cudaStream_t st);
+    int fork_lanes(int nl, cudaStream_t st);
+    int join_lanes(int nl, cudaStream_t st);
+    int64_t lane_bytes_for(int64_t head_mark, int64_t B, int64_t N, bool collapsed, cudaStream_t st);
 
 protected:
+    // Set by plan() for the chunk run_body is about to enqueue (read on the host at launch time only):
+    // pool_extra (per cloud of the chunk, device) = weight of the chunk's last point beyond 1 for average pooling,
+    // null when the clouds are not collapsed.
+    struct ChunkInfo {
+        const float *pool_extra = nullptr;
+    } cur_;
+    // Collapse support: < 0 = the forward depends on multiplicities in a way collapse.cu does not carry (FPS /
+    // ball query / density models); otherwise the number of copies of the collapsed location a cloud must keep
+    // (k for a k-nearest-neighbour graph, 1 for point-wise networks with max pooling).
+    virtual int collapse_copies() const { return -1; }
     // width of the pooled per-cloud feature the body hands to the head
     virtual int pooled_dim() const = 0;
     // body: point-wise layers + pooling for a chunk of Bc clouds -> pooled (Bc, pooled_dim())

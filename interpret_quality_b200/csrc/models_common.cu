@@ -15,6 +15,42 @@ static thread_local std::string t_error;
 void set_error(const std::string &msg) { t_error = msg; }
 const char *last_error() { return t_error.c_str(); }
 
+int ensure_dynamic_smem(const void *func, int bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> granted;
+    int dev = 0;
+    IQ_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int &have = granted[std::make_pair(func, dev)];
+    if (bytes > have) {
+        IQ_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return 0;
+}
+
+static std::mutex g_env_mu;
+static std::map<std::string, int> g_env_seen;
+void env_forget()
+{
+    std::lock_guard<std::mutex> lock(g_env_mu);
+    g_env_seen.clear();
+}
+
+int env_int(const char *name, int fallback)
+{
+    std::mutex &mu = g_env_mu;
+    std::map<std::string, int> &seen = g_env_seen;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = seen.find(name);
+    if (it != seen.end()) return it->second;
+    const char *v = getenv(name);
+    const int r = v ? (*v ? atoi(v) : 1) : fallback;
+    seen[name] = r;
+    return r;
+}
+
 // ---- profiling
 namespace {
 struct ProfEntry { const char *name; cudaEvent_t a, b; };
@@ -144,6 +180,62 @@ Model::~Model()
         if (join_ev_[i]) cudaEventDestroy(join_ev_[i]);
     }
     if (fork_ev_) cudaEventDestroy(fork_ev_);
+    if (host_meta_) cudaFreeHost(host_meta_);
+}
+
+// ---- chunk lanes: chunks of a forward are independent, so they are dealt round-robin to the caller's stream and
+// internal side streams, each lane with its own scratch; one chunk's kernel tails and pipeline fill overlap another's
+// steady state.
+static int lanes_wanted(int lanes)
+{
+    const int lanes_env = env_int("IQ_LANES", 0);
+    return std::min(std::max(lanes_env > 0 ? lanes_env : lanes, 1), (int)Model::MAX_LANES);
+}
+
+int Model::fork_lanes(int nl, cudaStream_t st)
+{
+    if (nl <= 1) return 0;
+    if (!fork_ev_) IQ_CUDA(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
+    IQ_CUDA(cudaEventRecord(fork_ev_, st));                         // the side lanes see everything queued so far
+    for (int l = 0; l < nl - 1; ++l) {
+        if (!side_[l]) {
+            IQ_CUDA(cudaStreamCreateWithFlags(&side_[l], cudaStreamNonBlocking));
+            IQ_CUDA(cudaEventCreateWithFlags(&join_ev_[l], cudaEventDisableTiming));
+        }
+        IQ_CUDA(cudaStreamWaitEvent(side_[l], fork_ev_, 0));
+    }
+    return 0;
+}
+
+// the head (and the caller) wait for every lane; also run on the error path so that no side stream is left
+// working on the scratch unobserved
+int Model::join_lanes(int nl, cudaStream_t st)
+{
+    for (int l = 0; l < nl - 1; ++l) {
+        if (!side_[l]) continue;
+        IQ_CUDA(cudaEventRecord(join_ev_[l], side_[l]));
+        IQ_CUDA(cudaStreamWaitEvent(st, join_ev_[l], 0));
+    }
+    return 0;
+}
+
+// clouds per chunk when the clouds have n instead of N points: the chunk keeps its number of rows
+static int64_t chunk_for(int64_t chunk, int64_t N, int64_t n) { return std::max<int64_t>(1, chunk * N / n); }
+
+// scratch of one lane: the largest chunk this forward can enqueue
+int64_t Model::lane_bytes_for(int64_t head_mark, int64_t B, int64_t N, bool collapsed, cudaStream_t st)
+{
+    int64_t most = 0;
+    for (int64_t n = collapsed ? 128 : N; n <= N; n += 128) {
+        Workspace probe;
+        probe.dry = true;
+        probe.off = head_mark;
+        if (run_body(probe, nullptr, 1, std::min<int64_t>(chunk_for(chunk, N, n), B), n, nullptr, nullptr, nullptr, st) != 0)
+            return -1;
+        most = std::max(most, round_up(probe.off, 256) - head_mark);
+        if (!collapsed) break;
+    }
+    return most;
 }
 
 int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,
@@ -151,48 +243,32 @@ int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64
 {
     float *pooled = ws.take<float>(B * pooled_dim());
     const int64_t head_mark = round_up(ws.off, 256);
-    // scratch of one chunk, measured on the largest one
     Workspace probe;
     probe.dry = true;
     probe.off = head_mark;
     if (int rc = run_body(probe, nullptr, point_major, std::min<int64_t>(chunk, B), N, nullptr, nullptr, nullptr, st)) return rc;
     const int64_t lane_bytes = round_up(probe.off, 256) - head_mark;
-    // Chunks are independent: with lanes > 1 they are dealt round-robin to the caller's stream and internal side
-    // streams, each lane with its own scratch, so one chunk's kernel tails and pipeline fill overlap another's
-    // steady state.
-    static const int lanes_env = getenv("IQ_LANES") ? atoi(getenv("IQ_LANES")) : 0;
-    const int want = std::min(std::max(lanes_env > 0 ? lanes_env : lanes, 1), (int)MAX_LANES);
-    const int nl = (int)std::min<int64_t>(want, ceil_div(B, chunk));
+    const int nl = (int)std::min<int64_t>(lanes_wanted(lanes), ceil_div(B, chunk));
     const int64_t body_end = head_mark + nl * lane_bytes;
     if (!ws.dry) {
         IQ_CHECK(body_end <= ws.size, "forward: workspace too small");
-        if (nl > 1) {
-            if (!fork_ev_) IQ_CUDA(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
-            IQ_CUDA(cudaEventRecord(fork_ev_, st));                 // the side lanes see everything queued so far
-            for (int l = 0; l < nl - 1; ++l) {
-                if (!side_[l]) {
-                    IQ_CUDA(cudaStreamCreateWithFlags(&side_[l], cudaStreamNonBlocking));
-                    IQ_CUDA(cudaEventCreateWithFlags(&join_ev_[l], cudaEventDisableTiming));
-                }
-                IQ_CUDA(cudaStreamWaitEvent(side_[l], fork_ev_, 0));
-            }
-        }
+        if (int rc = fork_lanes(nl, st)) return rc;
+        cur_ = ChunkInfo();
+        int rc = 0;
         int64_t i = 0;
-        for (int64_t b0 = 0; b0 < B; b0 += chunk, ++i) {
+        for (int64_t b0 = 0; b0 < B && rc == 0; b0 += chunk, ++i) {
             const int64_t Bc = std::min<int64_t>(chunk, B - b0);
             const int lane = (int)(i % nl);
             Workspace lw = ws;
             lw.off = head_mark + lane * lane_bytes;
             lw.size = head_mark + (lane + 1) * lane_bytes;
-            const int rc = run_body(lw, x + b0 * N * 3, point_major, Bc, N, pooled + b0 * pooled_dim(),
-                                    aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
-                                    aux_crt ? aux_crt + b0 * 1024 : nullptr, lane == 0 ? st : side_[lane - 1]);
-            if (rc != 0) return rc;
+            rc = run_body(lw, x + b0 * N * 3, point_major, Bc, N, pooled + b0 * pooled_dim(),
+                          aux_trans_feat ? aux_trans_feat + b0 * 64 * 64 : nullptr,
+                          aux_crt ? aux_crt + b0 * 1024 : nullptr, lane == 0 ? st : side_[lane - 1]);
         }
-        for (int l = 0; l < nl - 1; ++l) {                            // the head (and the caller) wait for every lane
-            IQ_CUDA(cudaEventRecord(join_ev_[l], side_[l]));
-            IQ_CUDA(cudaStreamWaitEvent(st, join_ev_[l], 0));
-        }
+        const int jrc = join_lanes(nl, st);
+        if (rc != 0) return rc;
+        if (jrc != 0) return jrc;
     }
     ws.off = head_mark;
     const int rc = run_head(ws, pooled, B, logits, st);
@@ -201,16 +277,115 @@ int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64
     return 0;
 }
 
+// The collapsed forward (collapse.cu): count the kept points per cloud, group the clouds by compacted size, rewrite
+// them, run every group through run_body at its own number of points, the head over all clouds, and hand the logits
+// back in the caller's order.  One host round trip (the kept counts) decides the grouping.
+int Model::plan_collapsed(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,
+                          const float *loc, cudaStream_t st)
+{
+    const int copies = std::max(collapse_copies(), 1);
+    const int pd = pooled_dim();
+    float *pooled = ws.take<float>(B * pd);
+    float *slog = ws.take<float>(B * num_classes);
+    int32_t *kept = ws.take<int32_t>(B);
+    int32_t *meta = ws.take<int32_t>(3 * B);                         // src | row_off | size, in sorted order
+    float *extra = ws.take<float>(B);
+    float *xc = ws.take<float>(B * N * 3);
+    const int64_t head_mark = round_up(ws.off, 256);
+    const int64_t lane_bytes = lane_bytes_for(head_mark, B, N, true, st);
+    if (lane_bytes < 0) return -1;
+    const int want = lanes_wanted(lanes);
+    if (ws.dry) {
+        ws.off = head_mark;
+        if (int rc = run_head(ws, nullptr, B, nullptr, st)) return rc;
+        ws.off = std::max(head_mark + std::min<int64_t>(want, B) * lane_bytes, ws.off);
+        return 0;
+    }
+    IQ_CHECK(B * N < ((int64_t)1 << 31), "forward: too many rows for one collapsed call");
+    if (host_meta_cap_ < 5 * B) {
+        if (host_meta_) cudaFreeHost(host_meta_);
+        host_meta_ = nullptr;
+        host_meta_cap_ = 0;
+        IQ_CUDA(cudaMallocHost(reinterpret_cast<void **>(&host_meta_), sizeof(int32_t) * 5 * B));
+        host_meta_cap_ = 5 * B;
+    }
+    if (int rc = launch_collapse_count(x, point_major, B, N, loc, kept, st)) return rc;
+    int32_t *h_kept = host_meta_, *h_src = host_meta_ + B, *h_off = host_meta_ + 2 * B, *h_size = host_meta_ + 3 * B;
+    float *h_extra = reinterpret_cast<float *>(host_meta_ + 4 * B);
+    IQ_CUDA(cudaMemcpyAsync(h_kept, kept, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    IQ_CUDA(cudaStreamSynchronize(st));
+    // counting sort by compacted size, largest first
+    const int nb = (int)(N / 128);
+    std::vector<int64_t> count(nb + 1, 0), start(nb + 2, 0);
+    auto size_of = [&](int32_t U) -> int64_t {
+        const int64_t M = N - U;
+        return M <= 0 ? N : std::min<int64_t>(N, round_up(U + std::min<int64_t>(M, copies), 128));
+    };
+    for (int64_t b = 0; b < B; ++b) count[size_of(h_kept[b]) / 128] += 1;
+    for (int t = nb; t >= 1; --t) start[t - 1] = start[t] + count[t];     // start[t] = first sorted position of size 128*t
+    std::vector<int64_t> fill(start.begin(), start.end());
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t n = size_of(h_kept[b]);
+        const int64_t s = fill[n / 128]++;
+        h_src[s] = (int32_t)b;
+        h_size[s] = (int32_t)n;
+        h_extra[s] = (float)((N - h_kept[b]) - (n - h_kept[b]));            // M - m: copies not materialised
+    }
+    int64_t rows = 0;
+    for (int64_t s = 0; s < B; ++s) { h_off[s] = (int32_t)rows; rows += h_size[s]; }
+    last_row_fraction = (double)rows / (double)(B * N);
+    last_buckets.assign(count.begin() + 1, count.end());
+    IQ_CUDA(cudaMemcpyAsync(meta, h_src, sizeof(int32_t) * 3 * B, cudaMemcpyHostToDevice, st));
+    IQ_CUDA(cudaMemcpyAsync(extra, h_extra, sizeof(float) * B, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_collapse_compact(x, point_major, B, N, loc, meta, meta + B, meta + 2 * B, xc, st)) return rc;
+
+    int64_t nchunks = 0;
+    for (int t = nb; t >= 1; --t) nchunks += ceil_div(count[t], chunk_for(chunk, N, 128 * t));
+    const int nl = (int)std::min<int64_t>(std::min<int64_t>(want, B), nchunks);
+    IQ_CHECK(head_mark + nl * lane_bytes <= ws.size, "forward: workspace too small");
+    if (int rc = fork_lanes(nl, st)) return rc;
+    int rc = 0;
+    int64_t i = 0;
+    for (int t = nb; t >= 1 && rc == 0; --t) {
+        const int64_t n = 128 * t, cn = chunk_for(chunk, N, n);
+        for (int64_t s0 = start[t]; s0 < start[t] + count[t] && rc == 0; s0 += cn, ++i) {
+            const int64_t Bc = std::min<int64_t>(cn, start[t] + count[t] - s0);
+            const int lane = (int)(i % nl);
+            Workspace lw = ws;
+            lw.off = head_mark + lane * lane_bytes;
+            lw.size = head_mark + (lane + 1) * lane_bytes;
+            cur_.pool_extra = extra + s0;
+            rc = run_body(lw, xc + (int64_t)h_off[s0] * 3, 1, Bc, n, pooled + s0 * pd, nullptr, nullptr,
+                          lane == 0 ? st : side_[lane - 1]);
+        }
+    }
+    cur_ = ChunkInfo();
+    const int jrc = join_lanes(nl, st);
+    if (rc != 0) return rc;
+    if (jrc != 0) return jrc;
+    ws.off = head_mark;
+    if (int hrc = run_head(ws, pooled, B, slog, st)) return hrc;
+    return launch_scatter_rows(slog, meta, B, num_classes, logits, st);
+}
+
 int64_t Model::workspace_bytes(int64_t B, int64_t N)
 {
+    B = std::max<int64_t>(B, 1);
     Workspace ws;
     ws.dry = true;
-    if (plan(ws, nullptr, 1, std::max<int64_t>(B, 1), N, nullptr, nullptr, nullptr, nullptr) != 0) return -1;
-    return round_up(ws.off, 256) + 256;
+    if (plan(ws, nullptr, 1, B, N, nullptr, nullptr, nullptr, nullptr) != 0) return -1;
+    int64_t need = ws.off;
+    if (collapse_copies() >= 0 && N % 128 == 0 && N >= 128) {          // a collapsed forward may be asked for as well
+        Workspace wc;
+        wc.dry = true;
+        if (plan_collapsed(wc, nullptr, 1, B, N, nullptr, nullptr, nullptr) != 0) return -1;
+        need = std::max(need, wc.off);
+    }
+    return round_up(need, 256) + 256;
 }
 
 int Model::forward(const float *x, int point_major, int64_t B, int64_t N, float *logits, void *wsp, int64_t ws_bytes,
-                   float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st)
+                   float *aux_trans_feat, int64_t *aux_crt, const float *collapse_loc, cudaStream_t st)
 {
     if (B == 0) return 0;                                          // an empty batch has null tensors and nothing to do
     IQ_CHECK(x && logits, "forward: null input or output");
@@ -218,6 +393,12 @@ int Model::forward(const float *x, int point_major, int64_t B, int64_t N, float 
     Workspace ws;
     ws.base = reinterpret_cast<char *>(wsp);
     ws.size = ws_bytes;
+    last_row_fraction = 1.0;
+    last_buckets.assign((size_t)ceil_div(N, 128), 0);
+    last_buckets.back() = B;
+    const bool no_collapse = env_int("IQ_NO_COLLAPSE", 0) != 0;              // A/B switch for scripts and tests
+    if (collapse_loc && !no_collapse && collapse_copies() >= 0 && N % 128 == 0 && N >= 128 && !aux_trans_feat && !aux_crt)
+        return plan_collapsed(ws, x, point_major, B, N, logits, collapse_loc, st);
     return plan(ws, x, point_major, B, N, logits, aux_trans_feat, aux_crt, st);
 }
 

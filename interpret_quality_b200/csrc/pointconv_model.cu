@@ -305,7 +305,7 @@ protected:
         if (int rc = sgemm(new_xyz, 3, L.w1x, 3, nullptr, s.V, L.c1, cents, L.c1, 3, ACT_NONE, "sgemm_sa_centroid", st))
             return rc;
         const bool tc = engine == 1;
-        const bool fuse12 = tc && L.c2 <= 128 && rows % 128 == 0 && !getenv("IQ_TC_NO_GATHER");   // layers 1 + 2 in one kernel (gemm_tc.cu, gathered A)
+        const bool fuse12 = tc && L.c2 <= 128 && rows % 128 == 0 && !env_int("IQ_TC_NO_GATHER", 0);   // layers 1 + 2 in one kernel (gemm_tc.cu, gathered A)
         if (!fuse12)
             if (int rc = launch_group_sub_act(s.U, L.c1, s.V, L.c1, L.b1, s.idx, Bc, S, K, Nsrc, L.c1, ACT_RELU,
                                               tc ? nullptr : s.h1hi, tc ? s.h1hi : nullptr, tc ? s.h1lo : nullptr, L.c1, st))

@@ -88,7 +88,7 @@ protected:
                 // consumes it (gemm_tc.cu, gathered-A variant) and never written to HBM.  IQ_TC_NO_GATHER (tests) takes the
                 // two-kernel route through H1; the results are bitwise the same.
                 TcGemm a;
-                if (getenv("IQ_TC_NO_GATHER")) {
+                if (env_int("IQ_TC_NO_GATHER", 0)) {
                     if (int rc = launch_group_sub_act(U + sc.col1, sa.c1_total, V + sc.col1, sa.c1_total, sc.b1, gidx, Bc, S,
                                                       sc.K, Nsrc, sc.c1, ACT_RELU, nullptr, h1hi, h1lo, sc.c1, st))
                         return rc;

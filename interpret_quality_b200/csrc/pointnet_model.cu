@@ -109,6 +109,8 @@ protected:
     }
 
     int pooled_dim() const override { return 1024; }
+    // point-wise layers + max pooling only: one copy of the collapsed location carries all of them (collapse.cu)
+    int collapse_copies() const override { return 1; }
 
     int run_head(Workspace &ws, const float *g, int64_t B, float *logits, cudaStream_t st) override
     {

@@ -6,8 +6,8 @@ import torch
 from . import ops
 from .tools.final_common import _device_of
 
-# contexts evaluated per internal pass; independent of args.interaction_batch_size
-ENGINE_CONTEXTS_PER_PASS = 128
+# masked clouds evaluated per internal pass (pairs x contexts x 4 coalitions); independent of args.interaction_batch_size
+ENGINE_CLOUDS_PER_PASS = 16384
 
 
 def compute_order_interaction_logits(model, data_disturb, region_id, region_pair_list, context_list, args,
@@ -18,31 +18,39 @@ def compute_order_interaction_logits(model, data_disturb, region_id, region_pair
     be 0, dtype may be float64 then).  Returns a float32 CUDA tensor (P, 4*ctx, C), rows 4k..4k+3 in
     the order above.  pair_slice (start, stop) restricts the work to a shard of the pairs (used by
     distributed.py); rows of other pairs are left zero.
+
+    The reference walks the pairs in a host loop and the contexts in batches of args.interaction_batch_size
+    (final_point_binary_interaction_logits.py:37-63); here ONE mask launch expands a whole block of pairs and ONE
+    forward evaluates its pairs x contexts x 4 clouds, each on its kept points only (iq_model_forward_coalitions).
     """
     dev = _device_of(model)
     R = int(getattr(args, "num_regions", 0) or int(np.max(region_id)) + 1)
     data = data_disturb.to(dev, torch.float32, non_blocking=True).reshape(-1, 3).contiguous()
     N = data.shape[0]
-    pairs = np.asarray(region_pair_list).astype(np.int64)
+    pairs = np.asarray(region_pair_list).astype(np.int64).reshape(-1, 2)
     ctxs = np.asarray(context_list)
     P, ctx = pairs.shape[0], ctxs.shape[1]
     m = ctxs.shape[2] if ctxs.ndim == 3 else 0
-    ctx_d = ops.to_dev_i64(ctxs.reshape(P, ctx, m), dev)
-    region_d = ops.to_dev_i64(region_id, dev)
-    center = ops.center(data)
     C = model.output_channels
     out = torch.zeros((P, 4 * ctx, C), dtype=torch.float32, device=dev)
     lo, hi = pair_slice if pair_slice is not None else (0, P)
-    step = ENGINE_CONTEXTS_PER_PASS
-    masked = torch.empty((4 * min(step, max(ctx, 1)), N, 3), dtype=torch.float32, device=dev)
+    if hi <= lo or ctx == 0:
+        return out
+    ctx_d = ops.to_dev_i64(ctxs.reshape(P, ctx, m)[lo:hi], dev)
+    pairs_d = ops.to_dev_i64(pairs[lo:hi], dev)
+    region_d = ops.to_dev_i64(region_id, dev)
+    center = ops.center(data)
+    pairs_per_pass = max(1, ENGINE_CLOUDS_PER_PASS // (4 * ctx))
+    masked = torch.empty((4 * ctx * min(pairs_per_pass, hi - lo), N, 3), dtype=torch.float32, device=dev)
+    flat = out.view(P * 4 * ctx, C)
     with torch.no_grad():
-        for p in range(lo, hi):
-            for s in range(0, ctx, step):
-                cb = ctx_d[p, s:s + step].contiguous()
-                rows = 4 * cb.shape[0]
-                ops.mask_interaction(data, center, cb, pairs[p, 0], pairs[p, 1], region_d, R, point_major=True,
-                                     out=masked[:rows])
-                model.forward_point_major(masked[:rows], out=out[p, 4 * s:4 * s + rows])
+        for p0 in range(0, hi - lo, pairs_per_pass):
+            np_ = min(pairs_per_pass, hi - lo - p0)
+            rows = 4 * ctx * np_
+            ops.mask_interaction_pairs(data, center, pairs_d[p0:p0 + np_], ctx_d[p0:p0 + np_], region_d, R,
+                                       point_major=True, out=masked[:rows])
+            model.forward_point_major(masked[:rows], out=flat[(lo + p0) * 4 * ctx:(lo + p0) * 4 * ctx + rows],
+                                      masked_to=center)
     return out
 
 

@@ -9,8 +9,11 @@ import torch
 from . import _lib
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _call(t, name, *args):
+    """Run one library entry on the device (and that device's current stream) of tensor `t`: the library launches on
+    the CUDA device that is current, so the guard keeps models / inputs on cuda:1 off cuda:0's stream."""
+    with torch.cuda.device(t.device):
+        _lib.check(getattr(_lib.load(), name)(*args, torch.cuda.current_stream(t.device).cuda_stream))
 
 
 def _chk(t, dtype, name):
@@ -38,7 +41,7 @@ def fps(xyz, npoint):
     if C != 3:
         raise ValueError("xyz must be (B,N,3)")
     out = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
-    _lib.check(_lib.load().iq_fps(xyz.data_ptr(), B, N, npoint, out.data_ptr(), _stream()))
+    _call(xyz, "iq_fps", xyz.data_ptr(), B, N, npoint, out.data_ptr())
     return out
 
 
@@ -48,7 +51,7 @@ def square_distance3(src, dst):
     B, N, _ = src.shape
     M = dst.shape[1]
     out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
-    _lib.check(_lib.load().iq_square_distance3(src.data_ptr(), dst.data_ptr(), B, N, M, out.data_ptr(), _stream()))
+    _call(src, "iq_square_distance3", src.data_ptr(), dst.data_ptr(), B, N, M, out.data_ptr())
     return out
 
 
@@ -57,8 +60,7 @@ def region_id(xyz, fps_index):
     _chk(fps_index, torch.int64, "fps_index")
     N = xyz.shape[-2]
     out = torch.empty((N,), dtype=torch.int64, device=xyz.device)
-    _lib.check(_lib.load().iq_region_id(xyz.data_ptr(), fps_index.data_ptr(), N, fps_index.numel(), out.data_ptr(),
-                                        _stream()))
+    _call(xyz, "iq_region_id", xyz.data_ptr(), fps_index.data_ptr(), N, fps_index.numel(), out.data_ptr())
     return out
 
 
@@ -66,7 +68,7 @@ def center(xyz):
     _chk(xyz, torch.float32, "xyz")
     N = xyz.shape[-2]
     out = torch.empty((3,), dtype=torch.float32, device=xyz.device)
-    _lib.check(_lib.load().iq_center(xyz.data_ptr(), N, out.data_ptr(), _stream()))
+    _call(xyz, "iq_center", xyz.data_ptr(), N, out.data_ptr())
     return out
 
 
@@ -87,8 +89,8 @@ def mask_shapley(data, center_t, orders, region_ids, out=None, in_place=False):
         if out is None:
             out = torch.empty(((R + 1) * bs, N, 3), dtype=torch.float32, device=data.device)
         dptr = data.data_ptr()
-    _lib.check(_lib.load().iq_mask_shapley(dptr, center_t.data_ptr(), orders.data_ptr(), region_ids.data_ptr(), bs, R,
-                                           N, out.data_ptr(), 1 if in_place else 0, _stream()))
+    _call(out, "iq_mask_shapley", dptr, center_t.data_ptr(), orders.data_ptr(), region_ids.data_ptr(), bs, R,
+                                           N, out.data_ptr(), 1 if in_place else 0)
     return out
 
 
@@ -105,9 +107,32 @@ def mask_interaction(data, center_t, contexts, region_i, region_j, region_ids, n
         shape = (4 * ctx, N, 3) if point_major else (4 * ctx, 3, N)
         out = torch.empty(shape, dtype=torch.float32, device=data.device)
     cptr = contexts.data_ptr() if contexts.numel() else 0
-    _lib.check(_lib.load().iq_mask_interaction(data.data_ptr(), center_t.data_ptr(), cptr, ctx, m, int(region_i),
+    _call(data, "iq_mask_interaction", data.data_ptr(), center_t.data_ptr(), cptr, ctx, m, int(region_i),
                                                int(region_j), region_ids.data_ptr(), num_regions, N,
-                                               1 if point_major else 0, out.data_ptr(), _stream()))
+                                               1 if point_major else 0, out.data_ptr())
+    return out
+
+
+def mask_interaction_pairs(data, center_t, pairs, contexts, region_ids, num_regions, point_major=True, out=None):
+    """data (N,3), pairs (P,2) i64, contexts (P,ctx,m) i64 -> (P*ctx*4, N, 3) (or (P*ctx*4, 3, N)): the
+    4-clouds-per-context blocks of every pair in one launch."""
+    _chk(data, torch.float32, "data")
+    _chk(center_t, torch.float32, "center")
+    _chk(pairs, torch.int64, "pairs")
+    _chk(contexts, torch.int64, "contexts")
+    _chk(region_ids, torch.int64, "region_id")
+    P, ctx, m = contexts.shape
+    if pairs.shape != (P, 2):
+        raise ValueError("pairs must be (P,2) with P = contexts.shape[0]")
+    N = region_ids.numel()
+    shape = (4 * P * ctx, N, 3) if point_major else (4 * P * ctx, 3, N)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=data.device)
+    elif out.numel() != 4 * P * ctx * N * 3:
+        raise ValueError("out must hold %s floats" % (shape,))
+    cptr = contexts.data_ptr() if contexts.numel() else 0
+    _call(data, "iq_mask_interaction_pairs", data.data_ptr(), center_t.data_ptr(), pairs.data_ptr(), cptr, P, ctx, m,
+          region_ids.data_ptr(), num_regions, N, 1 if point_major else 0, out.data_ptr())
     return out
 
 
@@ -116,8 +141,8 @@ def reward(logits, lbl, softmax_type="modified", out=None):
     B, C = logits.shape
     if out is None:
         out = torch.empty((B,), dtype=torch.float32, device=logits.device)
-    _lib.check(_lib.load().iq_reward(logits.data_ptr(), B, C, int(lbl), 1 if softmax_type == "normal" else 0,
-                                     out.data_ptr(), _stream()))
+    _call(logits, "iq_reward", logits.data_ptr(), B, C, int(lbl), 1 if softmax_type == "normal" else 0,
+                                     out.data_ptr())
     return out
 
 
@@ -128,7 +153,7 @@ def shapley_accumulate(v, orders, phi_sum):
     bs, R = orders.shape
     if v.numel() != bs * (R + 1) or phi_sum.numel() != R:
         raise ValueError("shape mismatch in shapley_accumulate")
-    _lib.check(_lib.load().iq_shapley_accumulate(v.data_ptr(), orders.data_ptr(), bs, R, phi_sum.data_ptr(), _stream()))
+    _call(v, "iq_shapley_accumulate", v.data_ptr(), orders.data_ptr(), bs, R, phi_sum.data_ptr())
     return phi_sum
 
 
@@ -137,8 +162,8 @@ def interaction_reduce(all_logits, lbl, softmax_type="modified"):
     P, rows, C = all_logits.shape
     ctx = rows // 4
     out = torch.empty((P, ctx), dtype=torch.float64, device=all_logits.device)
-    _lib.check(_lib.load().iq_interaction_reduce(all_logits.data_ptr(), P, ctx, C, int(lbl),
-                                                 1 if softmax_type == "normal" else 0, out.data_ptr(), _stream()))
+    _call(all_logits, "iq_interaction_reduce", all_logits.data_ptr(), P, ctx, C, int(lbl),
+                                                 1 if softmax_type == "normal" else 0, out.data_ptr())
     return out
 
 
@@ -147,7 +172,7 @@ def knn_xyz(xyz, k):
     _chk(xyz, torch.float32, "xyz")
     B, N, _ = xyz.shape
     out = torch.empty((B, N, k), dtype=torch.int32, device=xyz.device)
-    _lib.check(_lib.load().iq_knn_xyz(xyz.data_ptr(), B, N, k, out.data_ptr(), _stream()))
+    _call(xyz, "iq_knn_xyz", xyz.data_ptr(), B, N, k, out.data_ptr())
     return out
 
 
@@ -158,8 +183,7 @@ def knn_features(x, k, return_counts=False):
     B, N, C = x.shape
     out = torch.empty((B, N, k), dtype=torch.int32, device=x.device)
     cnt = torch.empty((B, N), dtype=torch.int32, device=x.device) if return_counts else None
-    _lib.check(_lib.load().iq_knn_features(x.data_ptr(), B, N, C, k, out.data_ptr(), cnt.data_ptr() if return_counts else None,
-                                           _stream()))
+    _call(x, "iq_knn_features", x.data_ptr(), B, N, C, k, out.data_ptr(), cnt.data_ptr() if return_counts else None)
     return (out, cnt) if return_counts else out
 
 
@@ -190,11 +214,11 @@ def region_smoothness_epoch(data, data_orig, offsets, members, orient, var_ub, v
     iters = torch.empty((R,), dtype=torch.int32, device=data.device)
     last_var = torch.zeros((R, 3), dtype=torch.float32, device=data.device)
     flags = torch.zeros((R,), dtype=torch.int32, device=data.device)
-    _lib.check(_lib.load().iq_region_smoothness_epoch(
+    _call(data, "iq_region_smoothness_epoch", 
         data.data_ptr(), data_orig.data_ptr(), offsets.data_ptr(), members.data_ptr(), orient.data_ptr(), var_ub.data_ptr(),
         var_lb.data_ptr(), smoothness.data_ptr(), alive.data_ptr(), iters.data_ptr(), last_var.data_ptr(), flags.data_ptr(),
         N, R, int(max_region), SMOOTHNESS_MODES[mode], 1 if objective == "inc" else 0, float(step), float(enum_step),
-        float(dist_threshold), float(stop_ratio), int(max_iteration), 1 if clamp else 0, _stream()))
+        float(dist_threshold), float(stop_ratio), int(max_iteration), 1 if clamp else 0)
     return iters, last_var, flags
 
 
@@ -203,7 +227,7 @@ def topk_rows(keys, k, largest=True):
     _chk(keys, torch.float32, "keys")
     rows, N = keys.shape
     out = torch.empty((rows, k), dtype=torch.int32, device=keys.device)
-    _lib.check(_lib.load().iq_topk_rows(keys.data_ptr(), rows, N, N, k, 1 if largest else 0, out.data_ptr(), _stream()))
+    _call(keys, "iq_topk_rows", keys.data_ptr(), rows, N, N, k, 1 if largest else 0, out.data_ptr())
     return out
 
 
@@ -215,7 +239,7 @@ def linear(x, w, b=None, act=0, engine=0):
     N = w.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x.device)
     bp = _chk(b, torch.float32, "b").data_ptr() if b is not None else 0
-    _lib.check(_lib.load().iq_linear(x.data_ptr(), w.data_ptr(), bp, M, N, K, act, engine, y.data_ptr(), _stream()))
+    _call(x, "iq_linear", x.data_ptr(), w.data_ptr(), bp, M, N, K, act, engine, y.data_ptr())
     return y
 
 
@@ -229,9 +253,9 @@ def linear_pool(x, w, b, clouds, points, act=0, engine=0, want_mean=True, want_a
     mean = torch.empty((clouds, N), dtype=torch.float32, device=x.device) if want_mean else None
     arg = torch.empty((clouds, N), dtype=torch.int64, device=x.device) if want_arg else None
     bp = _chk(b, torch.float32, "b").data_ptr() if b is not None else 0
-    _lib.check(_lib.load().iq_linear_pool(x.data_ptr(), w.data_ptr(), bp, clouds, points, N, K, act, engine,
+    _call(x, "iq_linear_pool", x.data_ptr(), w.data_ptr(), bp, clouds, points, N, K, act, engine,
                                           mx.data_ptr(), mean.data_ptr() if want_mean else 0,
-                                          arg.data_ptr() if want_arg else 0, _stream()))
+                                          arg.data_ptr() if want_arg else 0)
     return mx, mean, arg
 
 
@@ -242,6 +266,6 @@ def ball_query(radius, nsample, xyz, new_xyz):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     out = torch.empty((B, S, nsample), dtype=torch.int32, device=xyz.device)
-    _lib.check(_lib.load().iq_ball_query(xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, float(radius), nsample,
-                                         out.data_ptr(), _stream()))
+    _call(xyz, "iq_ball_query", xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, float(radius), nsample,
+                                         out.data_ptr())
     return out

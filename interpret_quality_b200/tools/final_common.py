@@ -68,7 +68,7 @@ def shapley_partial_sums(model, data_disturb, lbl, region_id, orders, args, logi
         rows = o.shape[0] * (R + 1)
         ops.mask_shapley(data, center, o, region_d, out=masked[:rows])
         lg = logits_out[s * (R + 1):s * (R + 1) + rows]
-        model.forward_point_major(masked[:rows], out=lg)
+        model.forward_point_major(masked[:rows], out=lg, masked_to=center)
         ops.reward(lg, y, soft, out=v[:rows])
         ops.shapley_accumulate(v[:rows], o, phi_sum)
     return phi_sum, logits_out

@@ -89,3 +89,20 @@ def interaction_from_logits(all_logits, lbl, softmax_type="modified"):
         for kk in range(ctx):
             out[p, kk] = (v[4 * kk] + v[4 * kk + 3] - v[4 * kk + 1] - v[4 * kk + 2]).item()
     return out
+
+
+def interaction_float64_yardstick(model, sd, data, region_id, pairs, contexts, num_regions, lbl, softmax_type="modified", k=20):
+    """(P, ctx) interactions from a FLOAT64 evaluation of the network on the same fp32 masked clouds
+    interaction_logits() builds: the yardstick against which the rounding noise of an fp32 run (the reference's or
+    ours) is measured in the GPU tests (tests/_gates.py)."""
+    sd64 = {kk: torch.from_numpy(np.asarray(v)).double() if np.asarray(v).dtype == np.float32 else torch.from_numpy(np.asarray(v))
+            for kk, v in sd.items()}
+    real = nets.forward
+    torch.set_default_dtype(torch.float64)
+    try:
+        nets.forward = lambda model_, x, sd_, k_=20: real(model_, x.double(), sd64, k_)
+        lg = interaction_logits(model, sd, data, region_id, pairs, contexts, num_regions, 25, k)
+    finally:
+        nets.forward = real
+        torch.set_default_dtype(torch.float32)
+    return interaction_from_logits(lg, lbl, softmax_type)

@@ -10,6 +10,7 @@ for C in (64, 128):
     x = torch.from_numpy(rs.normal(size=(32, 1024, C)).astype(np.float32)).cuda()
     for dbg in (0, 1, 2, 3, 5):
         os.environ["IQ_KNN_DBG"] = str(dbg)
+        _lib.load().iq_debug_reload_env()
         for _ in range(2):
             ops.knn_features(x, 20)
         _lib.profile_enable(True)

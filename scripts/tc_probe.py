@@ -11,6 +11,7 @@ for (M, N, K) in ((32768, 512, 128), (32768, 128, 64), (32768, 1024, 512)):
     b = torch.zeros(N, device="cuda")
     for dbg in (0, 1):
         os.environ["IQ_TC_DBG"] = str(dbg)
+        _lib.load().iq_debug_reload_env()
         for _ in range(2):
             ops.linear(x, w, b, act=0, engine=1)
         _lib.profile_enable(True)

@@ -195,7 +195,8 @@ if __name__ == "__main__":
             geometry()
         elif n == "dgcnn_2048":
             model_golden("dgcnn", 2048, "dgcnn_2048")
-        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables", "smoothness", "interaction_pipeline"):
+        elif n in ("dgcnn_more", "poses", "gen_pair", "shap_run", "result_tables", "smoothness", "interaction_pipeline",
+                   "dgcnn_headline", "dgcnn_2048_4", "pointnet2_100", "c4_dgcnn", "c4_gcnn", "interactions_f64"):
             pass                                   # handled at the bottom of the file
         else:
             model_golden(n)
@@ -475,3 +476,99 @@ def interaction_pipeline():
 
 if __name__ == "__main__" and "interaction_pipeline" in sys.argv[1:]:
     interaction_pipeline()
+
+
+def wide_shapley(name, N, n_perm, bs, tag):
+    """<tag>.npz: shap_sampling_all_regions_batch of the unmodified reference over `n_perm` seed-replayed
+    permutations (logits of every masked cloud + phi): the headline call of BASELINE.json for DGCNN (100 x 33 =
+    3300 clouds), DGCNN at N = 2048 and PointNet++ at 100 permutations ("widen parity")."""
+    import time
+    model, margs = load_ref_model(name)
+    data, fps_idx, region_id = base_inputs(N)
+    orders = synthetic.make_orders(1000, R)[:n_perm]
+    args = types.SimpleNamespace(num_points=N, num_regions=R, shapley_batch_size=bs, num_samples=n_perm,
+                                 softmax_type="modified", model=name, device=torch.device("cpu"))
+    t0 = time.time()
+    with torch.no_grad():
+        phi, logits = ref_common.shap_sampling_all_regions_batch(model, data, torch.tensor([LBL]), region_id, orders, args)
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), shapley_phi=phi, shapley_logits=logits.numpy(),
+                        shapley_nperm=np.array(n_perm), N=np.array(N))
+    print(tag + ".npz written", logits.shape, "%.0fs of reference CPU time" % (time.time() - t0))
+
+
+def c4_interactions(name, P=8, max_contexts=12):
+    """c4_<model>.npz: BASELINE config C4 on the unmodified reference: P pairs x all 13 orders m in {0,1,2,3,6,...,27,30} x
+    up to `max_contexts` contexts: compute_order_interaction_logits + compute_order_interaction per order."""
+    import time
+    model, margs = load_ref_model(name)
+    data, fps_idx, region_id = base_inputs(1024)
+    pairs, contexts = synthetic.make_pairs_and_contexts(P, R, max_contexts=max_contexts)
+    iargs = types.SimpleNamespace(interaction_batch_size=25, model=name, softmax_type="modified")
+    out = {"pairs": pairs, "orders_m": np.array(sorted(contexts.keys()))}
+    t0 = time.time()
+    for m in sorted(contexts.keys()):
+        with torch.no_grad():
+            il = ref_il.compute_order_interaction_logits(model, data, region_id, pairs, contexts[m], iargs)
+        out["ctx_m%d" % m] = contexts[m].astype(np.int64)
+        out["logits_m%d" % m] = il.numpy()
+        out["inter_m%d" % m] = ref_ci.compute_order_interaction(il, torch.tensor([LBL]), iargs)
+    np.savez_compressed(os.path.join(HERE, "c4_%s.npz" % name), **out)
+    print("c4_%s.npz written, %.0fs of reference CPU time" % (name, time.time() - t0))
+
+
+if __name__ == "__main__":
+    for n in sys.argv[1:]:
+        if n == "dgcnn_headline":
+            wide_shapley("dgcnn", 1024, 100, 5, "dgcnn_headline")
+        elif n == "dgcnn_2048_4":
+            wide_shapley("dgcnn", 2048, 4, 1, "dgcnn_2048_4")
+        elif n == "pointnet2_100":
+            wide_shapley("pointnet2", 1024, 100, 5, "pointnet2_100")
+        elif n == "c4_dgcnn":
+            c4_interactions("dgcnn")
+        elif n == "c4_gcnn":
+            c4_interactions("gcnn")
+
+
+def interactions_f64():
+    """interactions_f64.npz: the float64 yardstick of every interaction golden -- the SAME masked clouds (fp32 masks,
+    fp32 centre) through a float64 evaluation of the network (oracle/nets.py, which tests/test_oracle_golden.py pins to
+    the reference).  |reference fp32 - float64| is the reference's own rounding noise on an interaction; the GPU tests
+    hold ours to max(1e-3 * max|I|, 2 x that noise) per order and print both.  Keys: <model>_m<m> for the small sets of
+    <model>.npz, c4_<model>_m<m> for c4_<model>.npz."""
+    import time
+    from oracle import coalition as oc
+    from oracle import nets
+    data, fps_idx, region_id = base_inputs(1024)
+    out = {}
+
+    def f64_interactions(name, pairs, ctx):
+        sd = synthetic.make_state_dict(name)
+        sd64 = {k: torch.from_numpy(v).double() if v.dtype == np.float32 else torch.from_numpy(v) for k, v in sd.items()}
+        torch.set_default_dtype(torch.float64)
+        try:
+            real = nets.forward
+            nets.forward = lambda model, x, sd_, k=20: real(model, x.double(), sd64, k)
+            lg = oc.interaction_logits(name, sd, data.numpy(), region_id, pairs, ctx, R, 25)
+        finally:
+            nets.forward = real
+            torch.set_default_dtype(torch.float32)
+        return oc.interaction_from_logits(lg, LBL)
+
+    t0 = time.time()
+    pairs, contexts = synthetic.make_pairs_and_contexts(2, R, orders_m=(0, 3, 30), max_contexts=4)
+    for name in ("pointnet", "dgcnn", "gcnn", "pointnet2", "pointconv"):
+        for m in (0, 3, 30):
+            out["%s_m%d" % (name, m)] = f64_interactions(name, pairs, contexts[m])
+        print(name, "small set done, %.0fs" % (time.time() - t0), flush=True)
+    for name in ("gcnn", "dgcnn"):
+        g = np.load(os.path.join(HERE, "c4_%s.npz" % name))
+        for m in g["orders_m"]:
+            out["c4_%s_m%d" % (name, m)] = f64_interactions(name, g["pairs"], g["ctx_m%d" % m])
+            print("c4", name, "m", m, "%.0fs" % (time.time() - t0), flush=True)
+    np.savez_compressed(os.path.join(HERE, "interactions_f64.npz"), **out)
+    print("interactions_f64.npz written")
+
+
+if __name__ == "__main__" and "interactions_f64" in sys.argv[1:]:
+    interactions_f64()

@@ -134,10 +134,27 @@ def test_forward_stays_inside_workspace_logits_and_input(name):
     got = out[:B * model.output_channels * 4].view(torch.float32).reshape(B, model.output_channels)
     assert torch.equal(got, want)
     assert torch.equal(xin[:x.numel() * 4].view(torch.float32).reshape(x.shape), x)          # the input is read-only
-    with torch.cuda.device(DEV):                                            # one byte short must be refused, not overrun
-        rc = lib.iq_model_forward(h, xin.data_ptr(), 1, B, N, out.data_ptr(), ws.data_ptr(), int(need) - 4096, 0, 0,
+    # the coalition entry (collapsed clouds, other chunking) under the same guard bands
+    center = torch.from_numpy(coalition.center_of(synthetic.make_cloud(1024))).to(DEV)
+    out.fill_(0)
+    with torch.cuda.device(DEV):
+        _lib.check(lib.iq_model_forward_coalitions(h, xin.data_ptr(), 1, B, N, center.data_ptr(), out.data_ptr(),
+                                                   ws.data_ptr(), int(need), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert intact(ws_whole) and intact(out_whole) and intact(in_whole)
+    got = out[:B * model.output_channels * 4].view(torch.float32).reshape(B, model.output_channels)
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    # iq_model_workspace_bytes covers both entries; a workspace too small for either must be refused, not overrun
+    short = int(need) // 3 // 256 * 256
+    with torch.cuda.device(DEV):
+        rc = lib.iq_model_forward(h, xin.data_ptr(), 1, B, N, out.data_ptr(), ws.data_ptr(), short, 0, 0,
                                   torch.cuda.current_stream().cuda_stream)
-    assert rc != 0 and "workspace" in _lib.last_error()
+        assert rc != 0 and "workspace" in _lib.last_error()
+        rc = lib.iq_model_forward_coalitions(h, xin.data_ptr(), 1, B, N, center.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                             short, torch.cuda.current_stream().cuda_stream)
+        assert rc != 0 and "workspace" in _lib.last_error()
+    torch.cuda.synchronize()
+    assert intact(ws_whole)
 
 
 def test_coalition_kernels_stay_inside_their_outputs():

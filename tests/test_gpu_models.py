@@ -13,6 +13,7 @@ from interpret_quality_b200.final_point_binary_interaction_logits import compute
 from interpret_quality_b200.final_shapley_value import cal_norm_factor
 from interpret_quality_b200.tools import final_common, final_util
 from oracle import coalition, geom, nets
+from _gates import interaction_gate
 
 pytestmark = pytest.mark.gpu
 R, LBL, TOL = 32, 3, 1e-3
@@ -88,9 +89,9 @@ def test_interaction_path_vs_reference_golden(golden, name):
         assert tuple(il.shape) == g["inter_logits_m%d" % m].shape
         assert relmax(il.cpu().numpy(), g["inter_logits_m%d" % m]) <= TOL
         inter = compute_order_interaction(il, torch.tensor([LBL]), a)
-        ref = g["inter_m%d" % m]
-        scale = max(np.abs(ref).max(), np.abs(g["shapley_phi"]).max())
-        assert np.abs(inter - ref).max() <= TOL * scale
+        err, bound = interaction_gate(inter, g["inter_m%d" % m], golden("interactions_f64")["%s_m%d" % (name, m)],
+                                      "%s m=%-2d" % (name, m))
+        assert err <= bound, (name, m, err, bound)
 
 
 @pytest.mark.parametrize("name", MODELS)
