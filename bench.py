@@ -340,10 +340,11 @@ def kernel_work(model, k, buckets):
         w["tc_conv"] = T(2.0 * rows * (64 * 128 * 3 + 64 * 64))
     elif model == "pointnet2":
         mac = lambda *terms: 2.0 * clouds * sum(r * ci * co for r, ci, co in terms)
-        w["tc_sa_mlp2"] = T(mac((8192, 32, 32), (16384, 64, 64), (65536, 64, 96), (4096, 64, 64),
-                                (8192, 128, 128), (16384, 128, 128)))
-        w["tc_sa_mlp3_pool"] = T(mac((8192, 32, 64), (16384, 64, 128), (65536, 96, 128), (4096, 64, 128),
-                                     (8192, 128, 256), (16384, 128, 256)))
+        l2 = ((8192, 32, 32), (16384, 64, 64), (65536, 64, 96), (4096, 64, 64), (8192, 128, 128), (16384, 128, 128))
+        l3 = ((8192, 32, 64), (16384, 64, 128), (65536, 96, 128), (4096, 64, 128), (8192, 128, 256), (16384, 128, 256))
+        w["tc_sa_chain"] = T(mac(*(l2 + l3)))                  # layers 2 + 3 of every scale in one kernel (chain_tc.cu)
+        w["tc_sa_mlp12"] = T(mac(*l2))                         # IQ_TC_NO_CHAIN route
+        w["tc_sa_mlp3_pool"] = T(mac(*l3))
     elif model == "pointconv":
         mac = lambda *terms: 2.0 * clouds * sum(r * ci * co for r, ci, co in terms)
         w["tc_sa_mlp2"] = T(mac((16384, 64, 64), (8192, 128, 128), (128, 256, 512)))

@@ -14,7 +14,7 @@ extern "C" {
 
 int iq_version(void) { return 100; }
 const char *iq_last_error(void) { return last_error(); }
-uint64_t iq_launch_count(void) { return g_launch_count; }
+uint64_t iq_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 int iq_debug_reload_env(void)
 {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace iq {
@@ -45,8 +46,8 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 // number of kernels this library has launched (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
-#define IQ_COUNT_LAUNCH() (++::iq::g_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;
+#define IQ_COUNT_LAUNCH() (::iq::g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch
 struct ProfileScope {

@@ -103,6 +103,25 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st);
 int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float *hi, float *lo, int64_t ldo,
                       cudaStream_t st);
 
+// chain_tc.cu -- one grouped shared MLP of a set-abstraction scale in one kernel:
+//   out[g] = max over the K rows of group g of relu(relu(relu(U[idx] - V + b1) W2^T + b2) W3^T + b3)
+struct SaChain {
+    const float *U = nullptr, *V = nullptr, *b1 = nullptr;   // layer 1 as in TcGemm::Gather (U per source point, V per centroid)
+    const int32_t *idx = nullptr;                            // (rows) source point of every grouped row
+    int64_t ldu = 0, ldv = 0;
+    int64_t rows = 0;                                        // clouds * S * K, multiple of 128
+    int K = 0, S = 0, nsrc = 0;                              // neighbours per centroid, centroids / source points per cloud
+    int C1 = 0, C2 = 0, C3 = 0;                              // layer widths
+    const float *W2_hi = nullptr, *W2_lo = nullptr, *b2 = nullptr;   // (C2, C1) tf32 split, leading dimension ldw2
+    const float *W3_hi = nullptr, *W3_lo = nullptr, *b3 = nullptr;   // (C3, C2)
+    int64_t ldw2 = 0, ldw3 = 0;
+    float *out = nullptr;                                    // (rows / K, ld_out)
+    int64_t ld_out = 0;
+    const char *tag = "tc_sa_chain";
+};
+bool sa_chain_supported(const SaChain &g);
+int launch_sa_chain(const SaChain &g, cudaStream_t st);
+
 // knn_tc.cu -- fused tcgen05 Gram + candidate selection + exact re-rank (feature-space kNN of DGCNN)
 constexpr int KNN_CAND_CAP = 64;      // most candidates per row the re-rank handles
 bool knn_features_tc_supported(int64_t N, int C, int k);

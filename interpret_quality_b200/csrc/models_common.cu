@@ -3,13 +3,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "model.cuh"
 
 namespace iq {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 static thread_local std::string t_error;
 void set_error(const std::string &msg) { t_error = msg; }
@@ -51,30 +52,36 @@ int env_int(const char *name, int fallback)
     return r;
 }
 
-// ---- profiling
+// ---- profiling (shared by every thread that uses the library: guarded by one mutex; the launch counter is atomic)
 namespace {
 struct ProfEntry { const char *name; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfEntry> g_prof;
-std::vector<const char *> g_rep_names;
+constexpr size_t PROF_CAP = 1 << 16;            // events kept per profiling session; later launches are not timed
 }  // namespace
 
 ProfileScope::ProfileScope(const char *name, cudaStream_t s) : slot(-1), st(s)
 {
-    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (!g_prof_on || g_prof.size() >= PROF_CAP) return;
     ProfEntry e;
     e.name = name;
-    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    if (cudaEventCreate(&e.a) != cudaSuccess) return;
+    if (cudaEventCreate(&e.b) != cudaSuccess) { cudaEventDestroy(e.a); return; }
     cudaEventRecord(e.a, st);
     g_prof.push_back(e);
     slot = (int)g_prof.size() - 1;
 }
 ProfileScope::~ProfileScope()
 {
-    if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, st);
 }
 void profile_enable(bool on)
 {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     for (auto &e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     g_prof.clear();
     g_prof_on = on;
@@ -82,6 +89,7 @@ void profile_enable(bool on)
 int profile_report(const char **names, double *ms, long long *counts, int cap)
 {
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     std::map<std::string, std::pair<double, long long>> acc;
     std::map<std::string, const char *> keep;
     for (auto &e : g_prof) {

@@ -345,11 +345,8 @@ protected:
             const int64_t warps = cents * (L.c3 / 128);
             IQ_CHECK(K % 4 == 0 && K <= 512, "pointconv: aggregate needs a neighbour count that is a multiple of 4");
             const size_t agg_smem = sizeof(float) * 16 * (size_t)K * 8;
-            static size_t agg_smem_set = 48 * 1024;
-            if (agg_smem > agg_smem_set) {
-                IQ_CUDA(cudaFuncSetAttribute(aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem));
-                agg_smem_set = agg_smem;
-            }
+            if (agg_smem > 48 * 1024)
+                if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&aggregate_kernel), (int)agg_smem)) return rc;
             aggregate_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, agg_smem, st>>>(
                 s.h3, s.wd, cents, K, L.c3, (to_lin && tc) ? nullptr : (to_lin ? s.agghi : agg_out),
                 (to_lin && tc) ? s.agghi : nullptr, (to_lin && tc) ? s.agglo : nullptr, 16 * (int64_t)L.c3);

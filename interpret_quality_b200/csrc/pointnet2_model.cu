@@ -87,6 +87,19 @@ protected:
                 // layers 1 and 2 in one kernel: H1 = relu(U[idx] - V + b1) is produced tile by tile inside the GEMM that
                 // consumes it (gemm_tc.cu, gathered-A variant) and never written to HBM.  IQ_TC_NO_GATHER (tests) takes the
                 // two-kernel route through H1; the results are bitwise the same.
+                // all three layers and the max over the group in one kernel (chain_tc.cu): H1 is gathered into the
+                // operand ring and H2 stays in TMEM as the A operand of layer 3, so neither touches HBM.
+                // IQ_TC_NO_CHAIN (tests, A/B runs) takes the two-kernel route below through H2 in HBM.
+                SaChain ch;
+                ch.U = U + sc.col1; ch.ldu = sa.c1_total; ch.V = V + sc.col1; ch.ldv = sa.c1_total; ch.b1 = sc.b1;
+                ch.idx = gidx; ch.rows = rows; ch.K = sc.K; ch.S = S; ch.nsrc = Nsrc; ch.C1 = sc.c1; ch.C2 = sc.c2; ch.C3 = sc.c3;
+                ch.W2_hi = sc.l2.w_hi; ch.W2_lo = sc.l2.w_lo; ch.b2 = sc.l2.b; ch.ldw2 = sc.c1;
+                ch.W3_hi = sc.l3.w_hi; ch.W3_lo = sc.l3.w_lo; ch.b3 = sc.l3.b; ch.ldw3 = sc.c2;
+                ch.out = out + out_col + sc.col3; ch.ld_out = ld_out;
+                if (sa_chain_supported(ch) && !env_int("IQ_TC_NO_CHAIN", 0) && !env_int("IQ_TC_NO_GATHER", 0)) {
+                    if (int rc = launch_sa_chain(ch, st)) return rc;
+                    continue;
+                }
                 TcGemm a;
                 if (env_int("IQ_TC_NO_GATHER", 0)) {
                     if (int rc = launch_group_sub_act(U + sc.col1, sa.c1_total, V + sc.col1, sa.c1_total, sc.b1, gidx, Bc, S,

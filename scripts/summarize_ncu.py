@@ -59,5 +59,46 @@ def full(fn):
         print()
 
 
+def table(fn):
+    """One row per kernel FAMILY of an `ncu --set full` report (the instance with the longest duration): duration,
+    tensor-pipe / issue / DRAM utilisation, DRAM bytes and rate, L2 hit rate, registers, grid."""
+    out = subprocess.run(["ncu", "-i", fn, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr = rd[0]
+    col = lambda name: next((i for i, h in enumerate(hdr) if h == name), None)
+    want = [("us", "gpu__time_duration.sum", 1e-3), ("tensor %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 1),
+            ("issue %", "sm__inst_issued.avg.pct_of_peak_sustained_active", 1), ("warps %", "sm__warps_active.avg.pct_of_peak_sustained_active", 1),
+            ("dram %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 1), ("dram rd MB", "dram__bytes_read.sum", None),
+            ("dram wr MB", "dram__bytes_write.sum", None), ("L2 hit %", "lts__t_sector_hit_rate.pct", 1),
+            ("regs", "launch__registers_per_thread", 1), ("grid", "launch__grid_size", 1)]
+    units = rd[1]
+    best = OrderedDict()
+    for row in rd[2:]:
+        name = row[col("Kernel Name")]
+        fam = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "").replace("iq::", ""))
+        t = float(row[col("gpu__time_duration.sum")].replace(",", "") or 0)
+        if fam not in best or t > best[fam][0]:
+            best[fam] = (t, row)
+    print("| kernel | " + " | ".join(w[0] for w in want) + " | GB/s |")
+    print("|---|" + "---:|" * (len(want) + 1))
+    for fam, (t, row) in sorted(best.items(), key=lambda kv: -kv[1][0]):
+        cells, byts, dur = [], 0.0, None
+        for label, metric, scale in want:
+            i = col(metric)
+            if i is None or row[i] == "":
+                cells.append("-")
+                continue
+            v = float(row[i].replace(",", ""))
+            u = units[i]
+            if metric.startswith("dram__bytes"):
+                v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
+                byts += v
+            elif metric == "gpu__time_duration.sum":
+                v *= {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(u, 1e-3)
+                dur = v
+            cells.append("%.1f" % v)
+        print("| %s | " % fam[:60] + " | ".join(cells) + " | %.0f |" % (byts / dur * 1e3 if dur else 0))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "table": table}[sys.argv[1]](sys.argv[2])

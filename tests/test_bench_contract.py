@@ -1,0 +1,46 @@
+"""bench.py's JSON contract on the CPU side: the reference arm (which runs without a GPU) prints one line with the keys
+the driver reads, and the config table covers BASELINE.json's configs."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_valid_line():
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C1", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "masked-coalition forwards/sec" and d["unit"] == "forwards/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("pointnet_") and "model" not in d["config"]
+    # the unmodified reference is used whenever it travelled with the repo
+    if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "tools", "final_common.py")):
+        assert d["cpu_baseline"]["kind"] == "reference"
+
+
+def test_config_table_covers_baseline_configs():
+    sys.path.insert(0, ROOT)
+    import bench
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert len(base["configs"]) == 5
+    for name in ("headline", "C1", "C2", "C3", "C4", "C5"):
+        assert name in bench.CONFIGS
+    assert bench.CONFIGS["headline"] == {"kind": "shapley", "model": "dgcnn", "points": 1024, "perms": 100}
+    assert bench.CONFIGS["C2"]["model"] == "pointnet2" and bench.CONFIGS["C2"]["perms"] == 1000
+    assert bench.CONFIGS["C3"]["points"] == 2048 and bench.CONFIGS["C5"]["model"] == "pointconv"
+    # work model: a collapsed batch does less work than the same clouds at full size, kernel by kernel
+    full = bench.kernel_work("dgcnn", 20, {1024: 100})
+    half = bench.kernel_work("dgcnn", 20, {512: 100})
+    for k in full:
+        assert half[k][1] <= full[k][1]
+    assert abs(half["tc_gram_knn_c64"][1] / full["tc_gram_knn_c64"][1] - 0.25) < 1e-9
+    assert abs(half["tc_conv5_pool"][1] / full["tc_conv5_pool"][1] - 0.5) < 1e-9

@@ -84,3 +84,30 @@ def test_batched_gram_keys_through_dgcnn_engine_switch():
     per_cloud = np.abs(tc - fp).max(1) / np.abs(fp).max()
     # a near-tie neighbour may be decided differently by the two kNN paths on a few clouds
     assert np.median(per_cloud) <= 1e-5 and per_cloud.max() <= 1e-3
+
+
+def test_pointnet2_chain_kernel_equals_two_kernel_route():
+    """chain_tc.cu (layers 1-2-3 + group max in one kernel, H2 kept in TMEM) against the round-1 route (gathered-A STORE
+    -> H2 in HBM -> POOL): the same 3xTF32 products, only the order of the two cross terms differs."""
+    import os
+    import types
+    from interpret_quality_b200 import _lib, synthetic
+    from interpret_quality_b200.tools import final_util
+    from oracle import coalition, geom
+    a = types.SimpleNamespace(model="pointnet2", k=20, dataset="shapenet", feature_transform=True, device="cuda:0")
+    model = final_util.build_model(a, synthetic.make_state_dict("pointnet2"))
+    data = synthetic.make_cloud(1024)
+    rid = geom.region_id(data[0], geom.fps(data, 32)[0])
+    masked = geom.mask_shapley(data[0], coalition.center_of(data), synthetic.make_orders(1, 32), rid)[::2]
+    x = torch.from_numpy(masked).to("cuda:0")
+    chained = model.forward_point_major(x).cpu().numpy()
+    os.environ["IQ_TC_NO_CHAIN"] = "1"
+    _lib.load().iq_debug_reload_env()
+    try:
+        two_kernels = model.forward_point_major(x).cpu().numpy()
+    finally:
+        del os.environ["IQ_TC_NO_CHAIN"]
+        _lib.load().iq_debug_reload_env()
+    err = np.abs(chained - two_kernels).max() / np.abs(two_kernels).max()
+    print("pointnet2 chain vs two-kernel route: %.2e of scale" % err)
+    assert err <= 2e-6
