@@ -196,6 +196,15 @@ int iq_linear_pool(const float *x_dev, const float *w_dev, const float *b_dev, i
                    int64_t N, int64_t K, int act, int engine, float *out_max_dev, float *out_mean_dev,
                    int64_t *out_arg_dev, void *stream);
 
+/* One grouped shared MLP of a PointNet++ set-abstraction scale (models/pointnet2.py:215-232) as a single kernel
+ * (csrc/chain_tc.cu), exported for unit tests:
+ *   out[g][:] = max over the K rows r of group g of relu(relu(relu(U[cloud*nsrc + idx[r]] - V[g] + b1) W2^T + b2) W3^T + b3)
+ * U (clouds*nsrc, C1), V (clouds*S, C1), idx (clouds*S*K) i32, W2 (C2, C1), W3 (C3, C2), out (clouds*S, C3);
+ * (C2, C3) in {(32,64), (64,128), (96,128), (128,256)}, K in {16, 32, 64, 128}, clouds*S*K a multiple of 128. */
+int iq_grouped_mlp_max(const float *U_dev, const float *V_dev, const float *b1_dev, const int32_t *idx_dev, int64_t clouds,
+                       int64_t S, int64_t K, int64_t nsrc, int64_t C1, const float *W2_dev, const float *b2_dev, int64_t C2,
+                       const float *W3_dev, const float *b3_dev, int64_t C3, float *out_dev, void *stream);
+
 /* One epoch of the geometry ascent / descent of final_smoothness_center_enum_all.py: update_region :184-243 for every
  * region whose alive flag is set (the loop over regions at :305-321), in one launch, a CTA per region.
  *   data (N,3) in/out, data_orig (N,3): the cloud being pushed and the undisturbed cloud;

@@ -51,6 +51,7 @@ SIGNATURES = {
     "iq_topk_rows": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "iq_linear": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "iq_linear_pool": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp]),
+    "iq_grouped_mlp_max": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "iq_model_set_engine": (_int, [_vp, _int]),
 }
 

@@ -318,6 +318,31 @@ int iq_linear_pool(const float *x, const float *w, const float *b, int64_t cloud
     return rc;
 }
 
+int iq_grouped_mlp_max(const float *U, const float *V, const float *b1, const int32_t *idx, int64_t clouds, int64_t S,
+                       int64_t K, int64_t nsrc, int64_t C1, const float *W2, const float *b2, int64_t C2, const float *W3,
+                       const float *b3, int64_t C3, float *out, void *stream)
+{
+    IQ_CHECK(U && V && b1 && idx && W2 && b2 && W3 && b3 && out, "iq_grouped_mlp_max: null pointer");
+    // unit-test path of chain_tc.cu: the weights are split into scratch here; the models keep them split
+    cudaStream_t st = as_stream(stream);
+    float *buf = nullptr;
+    const size_t n2 = (size_t)C2 * C1, n3 = (size_t)C3 * C2;
+    IQ_CUDA(cudaMalloc(&buf, sizeof(float) * 2 * (n2 + n3)));
+    int rc = launch_split_tf32(W2, C2, (int)C1, C1, buf, buf + n2, C1, st);
+    if (!rc) rc = launch_split_tf32(W3, C3, (int)C2, C2, buf + 2 * n2, buf + 2 * n2 + n3, C2, st);
+    SaChain ch;
+    ch.U = U; ch.ldu = C1; ch.V = V; ch.ldv = C1; ch.b1 = b1; ch.idx = idx; ch.rows = clouds * S * K; ch.K = (int)K;
+    ch.S = (int)S; ch.nsrc = (int)nsrc; ch.C1 = (int)C1; ch.C2 = (int)C2; ch.C3 = (int)C3;
+    ch.W2_hi = buf; ch.W2_lo = buf + n2; ch.b2 = b2; ch.ldw2 = C1;
+    ch.W3_hi = buf + 2 * n2; ch.W3_lo = buf + 2 * n2 + n3; ch.b3 = b3; ch.ldw3 = C2;
+    ch.out = out; ch.ld_out = C3;
+    if (!rc && !sa_chain_supported(ch)) { set_error("iq_grouped_mlp_max: unsupported shape"); rc = -1; }
+    if (!rc) rc = launch_sa_chain(ch, st);
+    cudaStreamSynchronize(st);
+    cudaFree(buf);
+    return rc;
+}
+
 int iq_model_set_engine(iq_model *m, int engine)
 {
     IQ_CHECK(m && (engine == 0 || engine == 1), "iq_model_set_engine: bad argument");

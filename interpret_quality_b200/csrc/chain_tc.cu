@@ -17,8 +17,9 @@
 //   warp 1        MMA issuer: layer 2 in SS mode (A = gathered tile in the ring), layer 3 in TS mode (A = TMEM)
 //   warps 2-5     epilogue: thread = row of the tile (TMEM lane)
 //   warps 6-17    gather warps: three groups of four, thread = row, taking layer-2 ring stages in turn
-// TMEM columns: [0, C2) layer-2 accumulator, overwritten by H2 hi; [128, 128 + C2) H2 lo; [256, 256 + C3) layer-3
-// accumulator.  3xTF32 split products as in gemm_tc.cu (Alo*Bhi + Ahi*Blo + Ahi*Bhi, small terms first).
+// TMEM columns: layer-2 accumulator, overwritten in place by H2 hi; H2 lo; layer-3 accumulator -- two layer-2 / H2 buffers
+// when 4*C2 + C3 <= 512 (the layer-2 MMAs of the next tile then run while this tile is converted), one at C2 = 128,
+// C3 = 256.  3xTF32 split products as in gemm_tc.cu (Alo*Bhi + Ahi*Blo + Ahi*Bhi, small terms first).
 #include "tc_ptx.cuh"
 #include "kernels.cuh"
 
@@ -43,6 +44,7 @@ struct ChainParams {
     const float *b2, *b3;        // folded biases of layers 2 and 3
     float *out;                  // (rows / gK, ld_out): max over each group of gK rows
     int64_t ld_out;
+    int dbg;                     // IQ_CHAIN_DBG (bisecting): 1 no layer-3 MMAs, 2 no H2 conversion, 4 no gather loads, 8 no layer-2 MMAs
 };
 
 template <int C2, int C3>
@@ -62,6 +64,31 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
 // the 128 epilogue threads only (named barrier 1), leaving barrier 0 to __syncthreads
 __device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// The four roles of a CTA walk the SAME sequence of ring segments.  With two layer-2 buffers in TMEM (NBUF = 2: 4*C2 + C3
+// <= 512 columns) the layer-2 MMAs of tile i+1 are issued BEFORE the layer-3 MMAs of tile i, so the tensor pipe works on
+// them while the epilogue warps convert / pool tile i:   L2(0) | L2(1) L3(0) | L2(2) L3(1) | ...   With one buffer
+// (C2 = 128, C3 = 256 fills TMEM) the sequence is L2(0) L3(0) L2(1) L3(1) ...  l2(tile, buffer, use) / l3(tile, buffer, use,
+// ordinal): `use` counts the uses of that buffer (barrier parity), `ordinal` the tiles of this CTA.
+template <int NBUF, typename F2, typename F3>
+__device__ __forceinline__ void chain_schedule(int first, int step, int n, F2 l2, F3 l3)
+{
+    if (first >= n) return;
+    if (NBUF == 2) {
+        l2(first, 0, 0);
+        int i = 0;
+        for (int u = first; u < n; u += step, ++i) {
+            if (u + step < n) l2(u + step, (i + 1) & 1, (i + 1) >> 1);
+            l3(u, i & 1, i >> 1, i);
+        }
+    } else {
+        int i = 0;
+        for (int u = first; u < n; u += step, ++i) {
+            l2(u, 0, i);
+            l3(u, 0, i, i);
+        }
+    }
+}
+
 template <int C2, int C3>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_constant__ CUtensorMap map_w2lo,
@@ -71,28 +98,32 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
     using S = ChainSmem<C2, C3>;
     static_assert(C2 % 32 == 0 && C2 <= 128 && C3 % 32 == 0 && C3 <= 256, "chain: widths out of range");
     constexpr int KB3 = C2 / TBK;                                           // layer-3 k-blocks
-    constexpr uint32_t A3_LO = 128, ACC3 = 256;
+    constexpr int NBUF = 4 * C2 + C3 <= 512 ? 2 : 1;                        // layer-2 accumulator / H2 buffers in TMEM
+    // TMEM columns: H2 hi (over the layer-2 accumulator) of buffer b at b*C2, H2 lo at LO + b*C2, layer-3 accumulator at ACC3
+    constexpr uint32_t LO = NBUF == 2 ? 2 * C2 : 128, ACC3 = NBUF == 2 ? 4 * C2 : 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float *pool_s = reinterpret_cast<float *>(smem + CH_STAGES * S::STAGE_BYTES);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + CH_STAGES * S::STAGE_BYTES + S::POOL_BYTES);
     uint64_t *empty_bar = full_bar + CH_STAGES;
-    uint64_t *acc2_full = empty_bar + CH_STAGES;
-    uint64_t *a3_ready = acc2_full + 1;
-    uint64_t *acc3_full = a3_ready + 1;
+    uint64_t *acc2_full = empty_bar + CH_STAGES;                            // [2]
+    uint64_t *a3_ready = acc2_full + 2;                                     // [2]
+    uint64_t *acc3_full = a3_ready + 2;
     uint64_t *acc3_empty = acc3_full + 1;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc3_empty + 1);
+    uint64_t *go = acc3_empty + 1;                                          // [3]: producer -> gather group "your slot is free"
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(go + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb2n = (p.C1 + TBK - 1) / TBK;                                 // layer-2 k-blocks (TMA zero-fills the K tail)
+    const int first = blockIdx.x, step = gridDim.x, n = p.num_units;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_w2hi); prefetch_tmap(&map_w2lo); prefetch_tmap(&map_w3hi); prefetch_tmap(&map_w3lo);
         for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
-        mbar_init(acc2_full, 1);
-        mbar_init(a3_ready, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc2_full[b], 1); mbar_init(&a3_ready[b], 4); }
         mbar_init(acc3_full, 1);
         mbar_init(acc3_empty, 4);
+        for (int g = 0; g < 3; ++g) mbar_init(&go[g], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -104,218 +135,242 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // ring position shared by every role: each thread advances it over all segments, whether it takes part or not
+    int stage = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() { if (++stage == CH_STAGES) { stage = 0; phase ^= 1; } };
+
     if (warp == 0) {
         // ---- TMA producer
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-            for (int kb = 0; kb < kb2n; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t *st = smem + stage * S::STAGE_BYTES;
-                if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&full_bar[stage], 2 * C2 * 128);
-                    tma_load_2d(st + 2 * CH_A_BYTES, &map_w2hi, &full_bar[stage], kb * TBK, 0);
-                    tma_load_2d(st + 2 * CH_A_BYTES + C2 * 128, &map_w2lo, &full_bar[stage], kb * TBK, 0);
+        // The producer visits every ring position, so its parity waits on the empty barriers are always exactly one phase
+        // back.  The gather groups only take part in every third layer-2 position: a parity wait of theirs on a slot could
+        // be two phases ahead (reads "free" too early) or two behind (waits for a phase that needs their own data), so the
+        // producer hands each layer-2 slot to its owner group through that group's own barrier instead.
+        int turn = 0;
+        chain_schedule<NBUF>(first, step, n,
+            [&](int, int, int) {
+                for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == 3 ? 0 : turn + 1) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * S::STAGE_BYTES;
+                    if (elect_one_sync()) {
+                        mbar_arrive(&go[turn]);
+                        mbar_arrive_expect_tx(&full_bar[stage], 2 * C2 * 128);
+                        tma_load_2d(st + 2 * CH_A_BYTES, &map_w2hi, &full_bar[stage], kb * TBK, 0);
+                        tma_load_2d(st + 2 * CH_A_BYTES + C2 * 128, &map_w2lo, &full_bar[stage], kb * TBK, 0);
+                    }
+                    __syncwarp();
+                    advance();
                 }
-                __syncwarp();
-                if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-            }
-            for (int kb = 0; kb < KB3; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t *st = smem + stage * S::STAGE_BYTES;
-                if (elect_one_sync()) {
-                    mbar_arrive_n(&full_bar[stage], 4);                      // the gather warps have no part in these stages
-                    mbar_arrive_expect_tx(&full_bar[stage], 2 * C3 * 128);
-                    tma_load_2d(st, &map_w3hi, &full_bar[stage], kb * TBK, 0);
-                    tma_load_2d(st + C3 * 128, &map_w3lo, &full_bar[stage], kb * TBK, 0);
+            },
+            [&](int, int, int, int) {
+                for (int kb = 0; kb < KB3; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * S::STAGE_BYTES;
+                    if (elect_one_sync()) {
+                        mbar_arrive_n(&full_bar[stage], 4);                  // the gather warps have no part in these stages
+                        mbar_arrive_expect_tx(&full_bar[stage], 2 * C3 * 128);
+                        tma_load_2d(st, &map_w3hi, &full_bar[stage], kb * TBK, 0);
+                        tma_load_2d(st + C3 * 128, &map_w3lo, &full_bar[stage], kb * TBK, 0);
+                    }
+                    __syncwarp();
+                    advance();
                 }
-                __syncwarp();
-                if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
+            });
     } else if (warp == 1) {
         // ---- MMA issuer
         constexpr uint32_t idesc2 = make_idesc(C2), idesc3 = make_idesc(C3);
-        int stage = 0;
-        uint32_t phase = 0, uphase = 0;
-        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, uphase ^= 1) {
-            for (int kb = 0; kb < kb2n; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
-                const uint64_t ahi = make_smem_desc(sbase), alo = make_smem_desc(sbase + CH_A_BYTES);
-                const uint64_t bhi = make_smem_desc(sbase + 2 * CH_A_BYTES);
-                const uint64_t blo = make_smem_desc(sbase + 2 * CH_A_BYTES + C2 * 128);
-                if (elect_one_sync()) {
+        chain_schedule<NBUF>(first, step, n,
+            [&](int, int buf, int) {
+                const uint32_t d2 = tmem_base + (uint32_t)(buf * C2);
+                for (int kb = 0; kb < kb2n; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint64_t ahi = make_smem_desc(sbase), alo = make_smem_desc(sbase + CH_A_BYTES);
+                    const uint64_t bhi = make_smem_desc(sbase + 2 * CH_A_BYTES);
+                    const uint64_t blo = make_smem_desc(sbase + 2 * CH_A_BYTES + C2 * 128);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint64_t ad = term == 0 ? alo : ahi;
-                        const uint64_t bd = term == 1 ? blo : bhi;
+                        for (int term = 0; term < 3; ++term) {
+                            if (p.dbg & 8) break;
+                            const uint64_t ad = term == 0 ? alo : ahi;
+                            const uint64_t bd = term == 1 ? blo : bhi;
 #pragma unroll
-                        for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
-                            const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                            umma_tf32(tmem_base, ad + koff, bd + koff, idesc2, (kb | term | ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
+                                const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                                umma_tf32(d2, ad + koff, bd + koff, idesc2, (kb | term | ks) != 0 ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == kb2n - 1) umma_commit(&acc2_full[buf]);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == kb2n - 1) umma_commit(acc2_full);
+                    __syncwarp();
+                    advance();
                 }
-                __syncwarp();
-                if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-            }
-            mbar_wait(a3_ready, uphase);                                     // H2 hi / lo parked in TMEM by the epilogue warps
-            mbar_wait(acc3_empty, uphase ^ 1);                               // the previous tile's pooling has read its accumulator
-            tc_fence_after();
-            for (int kb = 0; kb < KB3; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+            },
+            [&](int, int buf, int use, int ord) {
+                mbar_wait(&a3_ready[buf], (uint32_t)(use & 1));              // H2 hi / lo parked in TMEM by the epilogue warps
+                mbar_wait(acc3_empty, (uint32_t)((ord & 1) ^ 1));            // the previous tile's pooling has read its accumulator
                 tc_fence_after();
-                const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
-                const uint64_t bhi = make_smem_desc(sbase), blo = make_smem_desc(sbase + C3 * 128);
-                if (elect_one_sync()) {
+                const uint32_t a_hi = tmem_base + (uint32_t)(buf * C2), a_lo = tmem_base + LO + (uint32_t)(buf * C2);
+                for (int kb = 0; kb < KB3; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint64_t bhi = make_smem_desc(sbase), blo = make_smem_desc(sbase + C3 * 128);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint64_t bd = term == 1 ? blo : bhi;
+                        for (int term = 0; term < 3; ++term) {
+                            if (p.dbg & 1) break;
+                            const uint64_t bd = term == 1 ? blo : bhi;
 #pragma unroll
-                        for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
-                            const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                            umma_tf32_ts(tmem_base + ACC3, tmem_base + (term == 0 ? A3_LO : 0u) + (uint32_t)(kb * TBK + ks * UMMA_K),
-                                         bd + koff, idesc3, (kb | term | ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
+                                const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                                umma_tf32_ts(tmem_base + ACC3, (term == 0 ? a_lo : a_hi) + (uint32_t)(kb * TBK + ks * UMMA_K),
+                                             bd + koff, idesc3, (kb | term | ks) != 0 ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == KB3 - 1) umma_commit(acc3_full);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == KB3 - 1) umma_commit(acc3_full);
+                    __syncwarp();
+                    advance();
                 }
-                __syncwarp();
-                if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
+            });
     } else if (warp >= 6) {
-        // ---- gather warps: thread = row of the tile; the three groups of four warps take layer-2 stages in turn
+        // ---- gather warps: thread = row of the tile; the three groups of four warps take layer-2 stages in turn and are
+        // told by the producer (go[group], one phase per owned slot) when their slot is free
         const int r = ((int)threadIdx.x - 192) & 127, grp = ((int)threadIdx.x - 192) >> 7;
         const int sw = r & 7;
-        int stage = 0, turn = 0;
-        uint32_t phase = 0;
-        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-            const int64_t row = (int64_t)unit * TBM + r;
-            const int64_t cen = row / p.gK, cloud = cen / p.gS;
-            const float *u = p.gU + (cloud * p.gnsrc + __ldg(p.gidx + row)) * p.gldu;
-            const float *v = p.gV + cen * p.gldv;
-            for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == 3 ? 0 : turn + 1) {
-                if (turn != grp) {
-                    if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-                    continue;
-                }
-                float4 uu[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    uu[q] = kb * TBK + 4 * q < p.C1 ? __ldg(reinterpret_cast<const float4 *>(u + kb * TBK) + q)
-                                                    : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                const uint32_t hi_row = smem_u32(smem + stage * S::STAGE_BYTES) + (uint32_t)r * 128u;
-                const uint32_t lo_row = hi_row + CH_A_BYTES;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float h[4] = {0.0f, 0.0f, 0.0f, 0.0f}, l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    if (kb * TBK + 4 * q < p.C1) {
-                        const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + kb * TBK) + q);
-                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.b1 + kb * TBK) + q);
-                        const float x[4] = {apply_act((uu[q].x - vv.x) + bb.x, p.act1), apply_act((uu[q].y - vv.y) + bb.y, p.act1),
-                                            apply_act((uu[q].z - vv.z) + bb.z, p.act1), apply_act((uu[q].w - vv.w) + bb.w, p.act1)};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { h[e] = tf32_round(x[e]); l[e] = tf32_round(x[e] - h[e]); }
+        int turn = 0;
+        uint32_t my_phase = 0;
+        chain_schedule<NBUF>(first, step, n,
+            [&](int unit, int, int) {
+                const int64_t row = (int64_t)unit * TBM + r;
+                const int64_t cen = row / p.gK, cloud = cen / p.gS;
+                const float *u = p.gU + (cloud * p.gnsrc + __ldg(p.gidx + row)) * p.gldu;
+                const float *v = p.gV + cen * p.gldv;
+                for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == 3 ? 0 : turn + 1) {
+                    if (turn != grp) {
+                        advance();
+                        continue;
                     }
-                    const uint32_t off = (uint32_t)((q ^ sw) << 4);
-                    sts128(hi_row + off, h[0], h[1], h[2], h[3]);
-                    sts128(lo_row + off, l[0], l[1], l[2], l[3]);
+                    float4 uu[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        uu[q] = (kb * TBK + 4 * q < p.C1 && !(p.dbg & 4)) ? __ldg(reinterpret_cast<const float4 *>(u + kb * TBK) + q)
+                                                                          : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    mbar_wait(&go[grp], my_phase);
+                    my_phase ^= 1;
+                    const uint32_t hi_row = smem_u32(smem + stage * S::STAGE_BYTES) + (uint32_t)r * 128u;
+                    const uint32_t lo_row = hi_row + CH_A_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float h[4] = {0.0f, 0.0f, 0.0f, 0.0f}, l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        if (kb * TBK + 4 * q < p.C1) {
+                            const float4 vv = __ldg(reinterpret_cast<const float4 *>(v + kb * TBK) + q);
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.b1 + kb * TBK) + q);
+                            const float x[4] = {apply_act((uu[q].x - vv.x) + bb.x, p.act1), apply_act((uu[q].y - vv.y) + bb.y, p.act1),
+                                                apply_act((uu[q].z - vv.z) + bb.z, p.act1), apply_act((uu[q].w - vv.w) + bb.w, p.act1)};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { h[e] = tf32_round(x[e]); l[e] = tf32_round(x[e] - h[e]); }
+                        }
+                        const uint32_t off = (uint32_t)((q ^ sw) << 4);
+                        sts128(hi_row + off, h[0], h[1], h[2], h[3]);
+                        sts128(lo_row + off, l[0], l[1], l[2], l[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    advance();
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
-                if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-            }
-            for (int kb = 0; kb < KB3; ++kb)                                 // layer-3 stages belong to the producer alone
-                if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-        }
+            },
+            [&](int, int, int, int) {
+                for (int kb = 0; kb < KB3; ++kb) advance();                  // layer-3 slots belong to the producer alone
+            });
     } else {
         // ---- epilogue warps: thread = row of the tile = TMEM lane
         const int quad = warp & 3;                                          // TMEM lane quadrant = rows [32 * quad, 32 * quad + 32)
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint32_t uphase = 0;
-        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, uphase ^= 1) {
-            // layer-2 accumulator -> H2 = relu(acc + b2) -> tf32 hi over the accumulator, lo 128 columns further
-            mbar_wait(acc2_full, uphase);
-            tc_fence_after();
+        chain_schedule<NBUF>(first, step, n,
+            [&](int, int buf, int use) {
+                // layer-2 accumulator -> H2 = relu(acc + b2) -> tf32 hi over the accumulator, lo in the lo buffer
+                mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
+                tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < C2; c0 += 32) {
-                float v[32];
-                tmem_ld32(lane_base + c0, v);
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float y = fmaxf(v[i] + __ldg(p.b2 + c0 + i), 0.0f);
-                    const float h = tf32_round(y);
-                    hi[i] = __float_as_uint(h);
-                    lo[i] = __float_as_uint(tf32_round(y - h));
-                }
-                tmem_st32(lane_base + c0, hi);
-                tmem_st32(lane_base + A3_LO + c0, lo);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a3_ready);
-
-            // layer-3 accumulator -> relu(acc + b3) -> max over each group of gK rows -> out
-            mbar_wait(acc3_full, uphase);
-            tc_fence_after();
-            const int64_t grp0 = (int64_t)unit * (TBM / p.gK);               // first group of this tile (gK divides 128)
-#pragma unroll 1
-            for (int c0 = 0; c0 < C3; c0 += 32) {
-                float v[32];
-                tmem_ld32(lane_base + ACC3 + c0, v);
-                float mine = 0.0f;                                          // lane l keeps column c0 + l of its group
-                if (p.gK >= 32) {
+                for (int c0 = 0; c0 < C2; c0 += 32) {
+                    if (p.dbg & 2) break;
+                    float v[32];
+                    tmem_ld32(lane_base + (uint32_t)(buf * C2 + c0), v);
+                    uint32_t hi[32], lo[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float y = fmaxf(v[i] + __ldg(p.b3 + c0 + i), 0.0f);          // >= 0: uint order == float order
-                        const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
-                        if (lane == i) mine = __uint_as_float(m);
+                        const float y = fmaxf(v[i] + __ldg(p.b2 + c0 + i), 0.0f);
+                        const float h = tf32_round(y);
+                        hi[i] = __float_as_uint(h);
+                        lo[i] = __float_as_uint(tf32_round(y - h));
                     }
-                    if (p.gK == 32) {
-                        p.out[(grp0 + quad) * p.ld_out + c0 + lane] = mine;
-                    } else {
-                        pool_s[quad * C3 + c0 + lane] = mine;
-                    }
-                } else {                                                    // gK == 16: two groups per warp
-                    const uint32_t half = lane < 16 ? 0x0000ffffu : 0xffff0000u;
-                    float other = 0.0f;                                     // lanes hold columns l and l + 16 of their half's group
+                    tmem_st32(lane_base + (uint32_t)(buf * C2 + c0), hi);
+                    tmem_st32(lane_base + LO + (uint32_t)(buf * C2 + c0), lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a3_ready[buf]);
+            },
+            [&](int unit, int, int, int ord) {
+                // layer-3 accumulator -> relu(acc + b3) -> max over each group of gK rows -> out
+                mbar_wait(acc3_full, (uint32_t)(ord & 1));
+                tc_fence_after();
+                const int64_t grp0 = (int64_t)unit * (TBM / p.gK);           // first group of this tile (gK divides 128)
+#pragma unroll 1
+                for (int c0 = 0; c0 < C3; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(lane_base + ACC3 + c0, v);
+                    float mine = 0.0f;                                      // lane l keeps column c0 + l of its group
+                    if (p.gK >= 32) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float y = fmaxf(v[i] + __ldg(p.b3 + c0 + i), 0.0f);
-                        const uint32_t m = __reduce_max_sync(half, __float_as_uint(y));
-                        if ((lane & 15) == (i & 15)) { if (i < 16) mine = __uint_as_float(m); else other = __uint_as_float(m); }
+                        for (int i = 0; i < 32; ++i) {
+                            const float y = fmaxf(v[i] + __ldg(p.b3 + c0 + i), 0.0f);      // >= 0: uint order == float order
+                            const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+                            if (lane == i) mine = __uint_as_float(m);
+                        }
+                        if (p.gK == 32) p.out[(grp0 + quad) * p.ld_out + c0 + lane] = mine;
+                        else pool_s[quad * C3 + c0 + lane] = mine;
+                    } else {                                                // gK == 16: two groups per warp
+                        // REDUX returns one warp-uniform value, so the two half-warp groups are reduced one after the other
+                        // with the other half's lanes contributing the neutral 0 (ReLU outputs are >= 0)
+                        float other = 0.0f;                                 // lanes hold columns l and l + 16 of their half's group
+                        const bool upper = lane >= 16;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t y = __float_as_uint(fmaxf(v[i] + __ldg(p.b3 + c0 + i), 0.0f));
+                            const uint32_t m0 = __reduce_max_sync(0xffffffffu, upper ? 0u : y);
+                            const uint32_t m1 = __reduce_max_sync(0xffffffffu, upper ? y : 0u);
+                            const float m = __uint_as_float(upper ? m1 : m0);
+                            if ((lane & 15) == (i & 15)) { if (i < 16) mine = m; else other = m; }
+                        }
+                        float *o = p.out + (grp0 + quad * 2 + (lane >> 4)) * p.ld_out + c0 + (lane & 15);
+                        o[0] = mine;
+                        o[16] = other;
                     }
-                    float *o = p.out + (grp0 + quad * 2 + (lane >> 4)) * p.ld_out + c0 + (lane & 15);
-                    o[0] = mine;
-                    o[16] = other;
                 }
-            }
-            if (p.gK > 32) {                                                // groups of 64 / 128 rows: combine the warps' maxima
-                epilogue_sync();
-                const int per = p.gK / 32;                                  // warps per group
-                const int groups = 4 / per;
-                for (int t = (int)threadIdx.x - 64; t < groups * C3; t += 128) {
-                    const int g = t / C3, c = t - g * C3;
-                    float m = pool_s[(g * per) * C3 + c];
-                    for (int w = 1; w < per; ++w) m = fmaxf(m, pool_s[(g * per + w) * C3 + c]);
-                    p.out[(grp0 + g) * p.ld_out + c] = m;
+                if (p.gK > 32) {                                            // groups of 64 / 128 rows: combine the warps' maxima
+                    epilogue_sync();
+                    const int per = p.gK / 32;                              // warps per group
+                    const int groups = 4 / per;
+                    for (int t = (int)threadIdx.x - 64; t < groups * C3; t += 128) {
+                        const int g = t / C3, c = t - g * C3;
+                        float m = pool_s[(g * per) * C3 + c];
+                        for (int w = 1; w < per; ++w) m = fmaxf(m, pool_s[(g * per + w) * C3 + c]);
+                        p.out[(grp0 + g) * p.ld_out + c] = m;
+                    }
+                    epilogue_sync();                                        // pool_s is reused by the next tile
                 }
-                epilogue_sync();                                            // pool_s is reused by the next tile
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc3_empty);
-        }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc3_empty);
+            });
     }
 
     tc_fence_before();
@@ -364,6 +419,7 @@ int launch_sa_chain(const SaChain &g, cudaStream_t st)
     p.C1 = g.C1; p.num_units = (int)(g.rows / TBM); p.gK = g.K; p.gS = g.S; p.gnsrc = g.nsrc; p.act1 = ACT_RELU;
     p.gU = g.U; p.gV = g.V; p.b1 = g.b1; p.gidx = g.idx; p.gldu = g.ldu; p.gldv = g.ldv; p.b2 = g.b2; p.b3 = g.b3;
     p.out = g.out; p.ld_out = g.ld_out;
+    p.dbg = env_int("IQ_CHAIN_DBG", 0);
     if (g.C2 == 32) return launch_chain_variant<32, 64>(g, p, st);
     if (g.C2 == 64) return launch_chain_variant<64, 128>(g, p, st);
     if (g.C2 == 96) return launch_chain_variant<96, 128>(g, p, st);

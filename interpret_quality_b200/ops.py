@@ -269,3 +269,18 @@ def ball_query(radius, nsample, xyz, new_xyz):
     _call(xyz, "iq_ball_query", xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, float(radius), nsample,
                                          out.data_ptr())
     return out
+
+
+def grouped_mlp_max(U, V, b1, idx, clouds, S, K, W2, b2, W3, b3):
+    """max over each group of K rows of relu(relu(relu(U[idx] - V + b1) W2^T + b2) W3^T + b3): csrc/chain_tc.cu
+    (one PointNet++ set-abstraction scale, models/pointnet2.py:215-232).  U (clouds*nsrc, C1), V (clouds*S, C1),
+    idx (clouds*S*K) int32 -> (clouds*S, C3)."""
+    for t, n in ((U, "U"), (V, "V"), (b1, "b1"), (W2, "W2"), (b2, "b2"), (W3, "W3"), (b3, "b3")):
+        _chk(t, torch.float32, n)
+    _chk(idx, torch.int32, "idx")
+    C1, C2, C3 = U.shape[1], W2.shape[0], W3.shape[0]
+    nsrc = U.shape[0] // clouds
+    out = torch.empty((clouds * S, C3), dtype=torch.float32, device=U.device)
+    _call(U, "iq_grouped_mlp_max", U.data_ptr(), V.data_ptr(), b1.data_ptr(), idx.data_ptr(), clouds, S, K, nsrc, C1,
+          W2.data_ptr(), b2.data_ptr(), C2, W3.data_ptr(), b3.data_ptr(), C3, out.data_ptr())
+    return out

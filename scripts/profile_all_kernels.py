@@ -34,10 +34,13 @@ def model_of(name):
     return m
 
 
-BATCH = {"dgcnn": 330, "gcnn": 330, "pointnet": 330, "pointnet2": 66, "pointconv": 66}
+# one chunk lane per model and a PLAIN forward (every cloud at N points: one launch per kernel of the forward, with the
+# production tile shapes); IQ_PROFILE_COLLAPSED=1 profiles the collapsed forward instead (8 size groups: 8x the launches)
+BATCH = {"dgcnn": 148, "gcnn": 148, "pointnet": 330, "pointnet2": 33, "pointconv": 66}
+COLLAPSED = bool(os.environ.get("IQ_PROFILE_COLLAPSED"))
 models = {n: model_of(n) for n in fam if n != "coalition"}
 for n, m in models.items():                                    # warm-up outside the profiled range (workspace, handles)
-    m.forward_point_major(masked[:BATCH[n]], masked_to=cen)
+    m.forward_point_major(masked[:BATCH[n]], masked_to=cen if COLLAPSED else None)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 if "coalition" in fam:
@@ -50,8 +53,10 @@ if "coalition" in fam:
     v = ops.reward(logits, LBL)
     ops.shapley_accumulate(v, orders, phi)
     ops.interaction_reduce(ilog, LBL)
+    if "dgcnn" in models:            # the collapse kernels (count, compact, scatter) + one 640-point size group of DGCNN
+        models["dgcnn"].forward_point_major(masked[16:17].repeat(64, 1, 1).contiguous(), masked_to=cen)
 for n, m in models.items():
-    m.forward_point_major(masked[:BATCH[n]], masked_to=cen)
+    m.forward_point_major(masked[:BATCH[n]], masked_to=cen if COLLAPSED else None)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("profiled families:", fam)

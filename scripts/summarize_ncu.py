@@ -62,7 +62,8 @@ def full(fn):
 def table(fn):
     """One row per kernel FAMILY of an `ncu --set full` report (the instance with the longest duration): duration,
     tensor-pipe / issue / DRAM utilisation, DRAM bytes and rate, L2 hit rate, registers, grid."""
-    out = subprocess.run(["ncu", "-i", fn, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(fn).read() if fn.endswith(".csv") else subprocess.run(["ncu", "-i", fn, "--page", "raw", "--csv"],
+                                                                     capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
     hdr = rd[0]
     col = lambda name: next((i for i, h in enumerate(hdr) if h == name), None)

@@ -1,8 +1,8 @@
 """profiles/r2_traffic.json from the ncu CSV of scripts/r2_profile.sh (dram__bytes_read.sum + dram__bytes_write.sum and
-gpu__time_duration.sum of every launch of `bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline`): per kernel
-family the DRAM bytes per launch averaged over all captured launches of the full-size steps, which is what bench.py
-quotes as roofline.traffic next to its algorithmic bytes per launch (same averaging).
-   python scripts/traffic_from_ncu.py gpurun_out/<tag>_traffic.csv profiles/r2_traffic.json"""
+gpu__time_duration.sum of every launch of ONE headline step, scripts/profile_step.py): per kernel family the DRAM bytes
+per launch averaged over the step's launches, which is what bench.py quotes as roofline.traffic next to its algorithmic
+bytes per launch (same averaging), plus a launch-list table with each family's share of the step.
+   python scripts/traffic_from_ncu.py gpurun_out/<tag>_step.csv profiles/r2_traffic.json > profiles/r2_launches.md"""
 import csv, io, json, re, sys
 from collections import defaultdict
 
@@ -35,11 +35,19 @@ for i, m in per.items():
     a[1] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
     a[2] += m.get("gpu__time_duration.sum", 0.0)
 out = {"workload": "dgcnn_k20_shapley_100perm_x33clouds_N1024_R32",
-       "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
-                  "python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline",
-       "note": "averages over every launch of the run (parity gate of 4 permutations, warm-ups, timed and profiled steps); "
-               "kernel replay: cold caches, serialised",
+       "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+                  "--profile-from-start off python scripts/profile_step.py",
+       "note": "one step (100 permutations x 33 clouds, collapsed), averages over the step's launches of each kernel; kernel "
+               "replay: cold caches, serialised -- compare shares, not absolutes",
        "kernels": {k: {"launches": a[0], "dram_bytes_per_launch": a[1] / a[0], "avg_us": a[2] / a[0]} for k, a in agg.items()}}
 json.dump(out, open(dst, "w"), indent=1)
+tot = sum(v["avg_us"] * v["launches"] for v in out["kernels"].values())
+print("# ncu launch list of one headline step (DGCNN, 100 permutations x 33 clouds, collapsed)\n")
+print("`%s`\n" % out["command"])
+print("| kernel | launches | total us | avg us | share | dram MB / launch |")
+print("|---|---:|---:|---:|---:|---:|")
 for k, v in sorted(out["kernels"].items(), key=lambda kv: -kv[1]["avg_us"] * kv[1]["launches"]):
-    print("%-20s launches %5d  dram %8.1f MB/launch  %8.1f us/launch" % (k, v["launches"], v["dram_bytes_per_launch"] / 1e6, v["avg_us"]))
+    print("| %s | %d | %.1f | %.1f | %.1f%% | %.1f |" % (k, v["launches"], v["avg_us"] * v["launches"], v["avg_us"],
+                                                     100 * v["avg_us"] * v["launches"] / tot, v["dram_bytes_per_launch"] / 1e6))
+print("\ntotal %.1f us over %d launches (cold-cache, serialised kernel replay: compare shares, not absolutes)"
+      % (tot, sum(v["launches"] for v in out["kernels"].values())))

@@ -111,3 +111,29 @@ def test_pointnet2_chain_kernel_equals_two_kernel_route():
     err = np.abs(chained - two_kernels).max() / np.abs(two_kernels).max()
     print("pointnet2 chain vs two-kernel route: %.2e of scale" % err)
     assert err <= 2e-6
+
+
+@pytest.mark.parametrize("C1,C2,C3,K", [(32, 32, 64, 16), (64, 64, 128, 32), (64, 96, 128, 128), (64, 64, 128, 32),
+                                        (128, 128, 256, 64), (128, 128, 256, 128), (32, 32, 64, 128), (128, 128, 256, 16)])
+def test_chained_grouped_mlp_kernel(C1, C2, C3, K):
+    """csrc/chain_tc.cu alone on random data against a plain fp32 evaluation (torch, float64 accumulate): every
+    (widths, group size) combination PointNet++ MSG uses plus the corners of the supported range; several tiles per CTA."""
+    g = torch.Generator().manual_seed(C1 + C2 + C3 + K)
+    clouds, nsrc = 3, 200
+    S = 128 * 160 // K                                          # 160 tiles of 128 rows per cloud: > 148 CTAs, 3+ tiles each
+    U = torch.randn((clouds * nsrc, C1), generator=g).cuda()
+    V = torch.randn((clouds * S, C1), generator=g).cuda() * 0.5
+    b1 = torch.randn((C1,), generator=g).cuda() * 0.1
+    idx = torch.randint(0, nsrc, (clouds * S * K,), generator=g, dtype=torch.int32).cuda()
+    W2 = (torch.randn((C2, C1), generator=g) / C1 ** 0.5).cuda()
+    b2 = torch.randn((C2,), generator=g).cuda() * 0.1
+    W3 = (torch.randn((C3, C2), generator=g) / C2 ** 0.5).cuda()
+    b3 = torch.randn((C3,), generator=g).cuda() * 0.1
+    got = ops.grouped_mlp_max(U, V, b1, idx, clouds, S, K, W2, b2, W3, b3)
+    cloud_of = torch.arange(clouds * S * K, device="cuda") // (S * K)
+    h1 = torch.relu(U[cloud_of * nsrc + idx.long()] - V.repeat_interleave(K, 0) + b1)
+    h2 = torch.relu((h1.double() @ W2.double().T).float() + b2)
+    h3 = torch.relu((h2.double() @ W3.double().T).float() + b3)
+    want = h3.reshape(clouds * S, K, C3).max(1)[0]
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err <= 2e-5, err
