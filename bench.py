@@ -345,6 +345,9 @@ def kernel_work(model, k, buckets):
         w["tc_sa_chain"] = T(mac(*(l2 + l3)))                  # layers 2 + 3 of every scale in one kernel (chain_tc.cu)
         w["tc_sa_mlp12"] = T(mac(*l2))                         # IQ_TC_NO_CHAIN route
         w["tc_sa_mlp3_pool"] = T(mac(*l3))
+        w["tc_sa_point"] = T(mac((512, 324, 320)))             # sa2: [features ; xyz] W1cat^T per source point
+        w["tc_sa3"] = T(mac((128, 644, 256), (128, 256, 512)))
+        w["tc_sa3_pool"] = T(mac((128, 512, 1024)))
     elif model == "pointconv":
         mac = lambda *terms: 2.0 * clouds * sum(r * ci * co for r, ci, co in terms)
         w["tc_sa_mlp2"] = T(mac((16384, 64, 64), (8192, 128, 128), (128, 256, 512)))
@@ -655,7 +658,9 @@ def run_b200(a):
                     # pipe sees, against the dense TF32 rate measured at the start of this leg
                     k["mmas_per_logical_mac"] = mult
                     k["executed_tflops"] = ach * mult
-                    k["executed_frac_of_tf32_peak"] = ach * mult / tf32["tf32_tflops_sustained"] if mult > 1 else None
+                    # cuBLAS dense TF32 of this run: best-of-10 ("burst") and back-to-back ("sustained", power-capped clocks)
+                    k["executed_frac_of_tf32_peak"] = ach * mult / tf32["tf32_tflops"] if mult > 1 else None
+                    k["executed_frac_of_tf32_sustained"] = ach * mult / tf32["tf32_tflops_sustained"] if mult > 1 else None
                 kernels.append(k)
             breakdown["kernels"] = kernels
             if kernels:

@@ -15,8 +15,10 @@
 // Layout of a CTA (576 threads, one CTA per SM, persistent over 128-row tiles):
 //   warp 0        TMA producer: W2 k-blocks (layer-2 stages), then W3 k-blocks (layer-3 stages) through one ring
 //   warp 1        MMA issuer: layer 2 in SS mode (A = gathered tile in the ring), layer 3 in TS mode (A = TMEM)
-//   warps 2-5     epilogue: thread = row of the tile (TMEM lane)
-//   warps 6-17    gather warps: three groups of four, thread = row, taking layer-2 ring stages in turn
+//   warps 2-9     epilogue: thread = row of the tile (TMEM lane), two warps per lane quadrant sharing the column blocks
+//                 (with one warp per quadrant the conversion + pooling of a tile, not its MMAs, paced the kernel:
+//                 ncu 43 % tensor-pipe active)
+//   warps 10-17   gather warps: two groups of four, thread = row, taking layer-2 ring stages in turn
 // TMEM columns: layer-2 accumulator, overwritten in place by H2 hi; H2 lo; layer-3 accumulator -- two layer-2 / H2 buffers
 // when 4*C2 + C3 <= 512 (the layer-2 MMAs of the next tile then run while this tile is converted), one at C2 = 128,
 // C3 = 256.  3xTF32 split products as in gemm_tc.cu (Alo*Bhi + Ahi*Blo + Ahi*Bhi, small terms first).
@@ -29,7 +31,10 @@ using namespace tc;
 
 namespace {
 
-constexpr int CH_THREADS = 192 + 384;
+constexpr int CH_EPI_WARPS = 8;                        // two per TMEM lane quadrant, each taking every other 32-column block
+constexpr int CH_GROUPS = 2;                           // gather groups of four warps (thread = row of the tile)
+constexpr int CH_GATHER0 = 64 + 32 * CH_EPI_WARPS;     // first gather thread
+constexpr int CH_THREADS = CH_GATHER0 + 128 * CH_GROUPS;
 constexpr int CH_STAGES = 3;
 constexpr int CH_A_BYTES = TBM * TBK * 4;              // one gathered A tile (hi or lo) per k-block: 16 KB
 
@@ -61,8 +66,8 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
-// the 128 epilogue threads only (named barrier 1), leaving barrier 0 to __syncthreads
-__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// the epilogue threads only (named barrier 1), leaving barrier 0 to __syncthreads
+__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CH_EPI_WARPS) : "memory"); }
 
 // The four roles of a CTA walk the SAME sequence of ring segments.  With two layer-2 buffers in TMEM (NBUF = 2: 4*C2 + C3
 // <= 512 columns) the layer-2 MMAs of tile i+1 are issued BEFORE the layer-3 MMAs of tile i, so the tensor pipe works on
@@ -110,8 +115,8 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
     uint64_t *a3_ready = acc2_full + 2;                                     // [2]
     uint64_t *acc3_full = a3_ready + 2;
     uint64_t *acc3_empty = acc3_full + 1;
-    uint64_t *go = acc3_empty + 1;                                          // [3]: producer -> gather group "your slot is free"
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(go + 3);
+    uint64_t *go = acc3_empty + 1;                                          // [groups][2]: producer -> gather group "your slot is free"
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(go + 2 * CH_GROUPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb2n = (p.C1 + TBK - 1) / TBK;                                 // layer-2 k-blocks (TMA zero-fills the K tail)
@@ -120,10 +125,10 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_w2hi); prefetch_tmap(&map_w2lo); prefetch_tmap(&map_w3hi); prefetch_tmap(&map_w3lo);
         for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc2_full[b], 1); mbar_init(&a3_ready[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc2_full[b], 1); mbar_init(&a3_ready[b], CH_EPI_WARPS); }
         mbar_init(acc3_full, 1);
-        mbar_init(acc3_empty, 4);
-        for (int g = 0; g < 3; ++g) mbar_init(&go[g], 1);
+        mbar_init(acc3_empty, CH_EPI_WARPS);
+        for (int g = 0; g < 2 * CH_GROUPS; ++g) mbar_init(&go[g], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -145,20 +150,25 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
         // The producer visits every ring position, so its parity waits on the empty barriers are always exactly one phase
         // back.  The gather groups only take part in every third layer-2 position: a parity wait of theirs on a slot could
         // be two phases ahead (reads "free" too early) or two behind (waits for a phase that needs their own data), so the
-        // producer hands each layer-2 slot to its owner group through that group's own barrier instead.
+        // producer hands each layer-2 slot to its owner group through that group's own barriers instead.  The ring lets the
+        // producer run at most three positions -- one more slot of the same group -- ahead of the slot a group is working on,
+        // so a group alternates between two barriers (its j-th slot uses barrier j & 1, phase j >> 1): never more than one
+        // arrival outstanding per barrier.
         int turn = 0;
+        uint32_t owned[CH_GROUPS] = {};
         chain_schedule<NBUF>(first, step, n,
             [&](int, int, int) {
-                for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == 3 ? 0 : turn + 1) {
+                for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == CH_GROUPS ? 0 : turn + 1) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *st = smem + stage * S::STAGE_BYTES;
                     if (elect_one_sync()) {
-                        mbar_arrive(&go[turn]);
+                        mbar_arrive(&go[2 * turn + (int)(owned[turn] & 1u)]);
                         mbar_arrive_expect_tx(&full_bar[stage], 2 * C2 * 128);
                         tma_load_2d(st + 2 * CH_A_BYTES, &map_w2hi, &full_bar[stage], kb * TBK, 0);
                         tma_load_2d(st + 2 * CH_A_BYTES + C2 * 128, &map_w2lo, &full_bar[stage], kb * TBK, 0);
                     }
                     __syncwarp();
+                    ++owned[turn];
                     advance();
                 }
             },
@@ -237,20 +247,20 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
                     advance();
                 }
             });
-    } else if (warp >= 6) {
+    } else if (warp >= 2 + CH_EPI_WARPS) {
         // ---- gather warps: thread = row of the tile; the three groups of four warps take layer-2 stages in turn and are
         // told by the producer (go[group], one phase per owned slot) when their slot is free
-        const int r = ((int)threadIdx.x - 192) & 127, grp = ((int)threadIdx.x - 192) >> 7;
+        const int r = ((int)threadIdx.x - CH_GATHER0) & 127, grp = ((int)threadIdx.x - CH_GATHER0) >> 7;
         const int sw = r & 7;
         int turn = 0;
-        uint32_t my_phase = 0;
+        uint32_t mine_n = 0;                                                 // layer-2 slots this group has taken
         chain_schedule<NBUF>(first, step, n,
             [&](int unit, int, int) {
                 const int64_t row = (int64_t)unit * TBM + r;
                 const int64_t cen = row / p.gK, cloud = cen / p.gS;
                 const float *u = p.gU + (cloud * p.gnsrc + __ldg(p.gidx + row)) * p.gldu;
                 const float *v = p.gV + cen * p.gldv;
-                for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == 3 ? 0 : turn + 1) {
+                for (int kb = 0; kb < kb2n; ++kb, turn = turn + 1 == CH_GROUPS ? 0 : turn + 1) {
                     if (turn != grp) {
                         advance();
                         continue;
@@ -260,8 +270,8 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
                     for (int q = 0; q < 8; ++q)
                         uu[q] = (kb * TBK + 4 * q < p.C1 && !(p.dbg & 4)) ? __ldg(reinterpret_cast<const float4 *>(u + kb * TBK) + q)
                                                                           : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    mbar_wait(&go[grp], my_phase);
-                    my_phase ^= 1;
+                    mbar_wait(&go[2 * grp + (int)(mine_n & 1u)], (mine_n >> 1) & 1u);
+                    ++mine_n;
                     const uint32_t hi_row = smem_u32(smem + stage * S::STAGE_BYTES) + (uint32_t)r * 128u;
                     const uint32_t lo_row = hi_row + CH_A_BYTES;
 #pragma unroll
@@ -291,6 +301,8 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
     } else {
         // ---- epilogue warps: thread = row of the tile = TMEM lane
         const int quad = warp & 3;                                          // TMEM lane quadrant = rows [32 * quad, 32 * quad + 32)
+        const int half = (warp - 2) >> 2;                                   // which of the quadrant's warps: 32-column blocks half, half + 2, ...
+        constexpr int CSTEP = 32 * (CH_EPI_WARPS / 4);
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         chain_schedule<NBUF>(first, step, n,
             [&](int, int buf, int use) {
@@ -298,7 +310,7 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
                 mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
                 tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < C2; c0 += 32) {
+                for (int c0 = 32 * half; c0 < C2; c0 += CSTEP) {
                     if (p.dbg & 2) break;
                     float v[32];
                     tmem_ld32(lane_base + (uint32_t)(buf * C2 + c0), v);
@@ -324,7 +336,7 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
                 tc_fence_after();
                 const int64_t grp0 = (int64_t)unit * (TBM / p.gK);           // first group of this tile (gK divides 128)
 #pragma unroll 1
-                for (int c0 = 0; c0 < C3; c0 += 32) {
+                for (int c0 = 32 * half; c0 < C3; c0 += CSTEP) {
                     float v[32];
                     tmem_ld32(lane_base + ACC3 + c0, v);
                     float mine = 0.0f;                                      // lane l keeps column c0 + l of its group
@@ -359,7 +371,7 @@ sa_chain_kernel(const __grid_constant__ CUtensorMap map_w2hi, const __grid_const
                     epilogue_sync();
                     const int per = p.gK / 32;                              // warps per group
                     const int groups = 4 / per;
-                    for (int t = (int)threadIdx.x - 64; t < groups * C3; t += 128) {
+                    for (int t = (int)threadIdx.x - 64; t < groups * C3; t += 32 * CH_EPI_WARPS) {
                         const int g = t / C3, c = t - g * C3;
                         float m = pool_s[(g * per) * C3 + c];
                         for (int w = 1; w < per; ++w) m = fmaxf(m, pool_s[(g * per + w) * C3 + c]);

@@ -32,6 +32,7 @@ struct Scale {
 struct SaMsg {
     int npoint = 0, cin_feat = 0, c1_total = 0, cout_total = 0;
     float *w1cat = nullptr;      // (c1_total, ldw): first layers of the three scales over [features ; xyz ; pad]
+    float *w1cat_hi = nullptr, *w1cat_lo = nullptr;   // its tf32 split (tcgen05 path of the per-point product)
     float *w1x = nullptr;        // (c1_total, 3): their xyz columns (per-centroid term)
     int ldw = 0;
     Scale sc[3];
@@ -73,8 +74,16 @@ protected:
     {
         const int S = sa.npoint;
         if (int rc = launch_fps(src_xyz, Bc, Nsrc, S, nullptr, nullptr, new_xyz, st)) return rc;
-        if (int rc = sgemm(src_in, ld_in, sa.w1cat, sa.ldw, nullptr, U, sa.c1_total, Bc * Nsrc, sa.c1_total, kin,
-                           ACT_NONE, "sgemm_sa_point", st))
+        // U = [features ; xyz] W1cat^T per source point.  sa1 has K = 3 (SIMT); sa2's 324 -> 320 product runs on tcgen05:
+        // the source rows are split into tf32 hi / lo in the (then idle) grouped-activation scratch first
+        TcGemm pt;
+        pt.A_hi = h1hi; pt.A_lo = h1lo; pt.lda = ld_in; pt.B_hi = sa.w1cat_hi; pt.B_lo = sa.w1cat_lo; pt.ldb = sa.ldw;
+        pt.K = kin; pt.M = (int)(Bc * Nsrc); pt.N = sa.c1_total; pt.C = U; pt.ldc = sa.c1_total; pt.tag = "tc_sa_point";
+        if (engine == 1 && kin >= 32 && h1lo && tc_gemm_supported(pt)) {
+            if (int rc = launch_split_tf32(src_in, Bc * Nsrc, kin, ld_in, h1hi, h1lo, ld_in, st)) return rc;
+            if (int rc = launch_gemm_tc(pt, st)) return rc;
+        } else if (int rc = sgemm(src_in, ld_in, sa.w1cat, sa.ldw, nullptr, U, sa.c1_total, Bc * Nsrc, sa.c1_total, kin,
+                                  ACT_NONE, "sgemm_sa_point", st))
             return rc;
         if (int rc = sgemm(new_xyz, 3, sa.w1x, 3, nullptr, V, sa.c1_total, Bc * S, sa.c1_total, 3, ACT_NONE,
                            "sgemm_sa_centroid", st))
@@ -162,6 +171,8 @@ protected:
         float *l2 = ws.take<float>(Bc * S2 * 644);               // [xyz | 640 features | pad]
         float *a256 = ws.take<float>(Bc * S2 * 256);
         float *a512 = ws.take<float>(Bc * S2 * 512);
+        float *a256lo = engine == 1 ? ws.take<float>(Bc * S2 * 256) : nullptr;
+        float *a512lo = engine == 1 ? ws.take<float>(Bc * S2 * 512) : nullptr;
         float *pmax = ws.take<float>(Bc * 1024);
         IQ_CHECK(ws.ok(), "pointnet2: workspace too small");
         if (ws.dry) return 0;
@@ -178,6 +189,27 @@ protected:
             return rc;
         if (int rc = launch_copy_cols(xyz2, 3, Bc * S2, 3, l2, 644, 3, st)) return rc;
         if (int rc = launch_copy_cols(xyz2, 3, Bc * S2, 0, l2 + 643, 644, 1, st)) return rc;     // zero the pad column
+        if (engine == 1 && (Bc * S2) % 128 == 0) {
+            // group-all layer on tcgen05 (3xTF32): 644 -> 256 -> 512 as hi/lo STORE products, 512 -> 1024 with the max over
+            // the cloud's 128 points in the POOL epilogue (round 1 ran these three on the fp32 SIMT GEMM: 30 ms per 3300 clouds)
+            if (int rc = launch_split_tf32(l2, Bc * S2, 644, 644, h1hi, h1lo, 644, st)) return rc;
+            TcGemm a;
+            a.A_hi = h1hi; a.A_lo = h1lo; a.lda = 644; a.B_hi = s3a.w_hi; a.B_lo = s3a.w_lo; a.ldb = 644; a.K = 644;
+            a.M = (int)(Bc * S2); a.N = 256; a.C_hi = a256; a.C_lo = a256lo; a.ldc = 256; a.bias = s3a.b; a.act = ACT_RELU;
+            a.tag = "tc_sa3";
+            if (int rc = launch_gemm_tc(a, st)) return rc;
+            TcGemm b;
+            b.A_hi = a256; b.A_lo = a256lo; b.lda = 256; b.B_hi = s3b.w_hi; b.B_lo = s3b.w_lo; b.ldb = 256; b.K = 256;
+            b.M = (int)(Bc * S2); b.N = 512; b.C_hi = a512; b.C_lo = a512lo; b.ldc = 512; b.bias = s3b.b; b.act = ACT_RELU;
+            b.tag = "tc_sa3";
+            if (int rc = launch_gemm_tc(b, st)) return rc;
+            TcGemm c;
+            c.mode = 1;
+            c.A_hi = s3c.w_hi; c.A_lo = s3c.w_lo; c.lda = 512; c.B_hi = a512; c.B_lo = a512lo; c.ldb = 512; c.K = 512;
+            c.clouds = (int)Bc; c.points = S2; c.cout = 1024; c.out_max = pooled; c.ld_out = 1024; c.bias = s3c.b;
+            c.act = ACT_RELU; c.tag = "tc_sa3_pool";
+            return launch_gemm_tc(c, st);
+        }
         if (int rc = sgemm(l2, 644, s3a.w, 644, s3a.b, a256, 256, Bc * S2, 256, 644, ACT_RELU, "sgemm_sa3", st)) return rc;
         if (int rc = sgemm(a256, 256, s3b.w, 256, s3b.b, a512, 512, Bc * S2, 512, 256, ACT_RELU, "sgemm_sa3", st)) return rc;
         GemmDesc g;
@@ -240,7 +272,10 @@ bool make_sa(PointNet2Model *m, const StateDict &sd, const std::string &p, int n
         col1 += sc.c1;
         col3 += sc.c3;
     }
-    return up(m, w1cat, &sa.w1cat, err) && up(m, w1x, &sa.w1x, err);
+    std::vector<float> whi, wlo;
+    split_tf32_host(w1cat, whi, wlo);
+    return up(m, w1cat, &sa.w1cat, err) && up(m, w1x, &sa.w1x, err) && up(m, whi, &sa.w1cat_hi, err) &&
+           up(m, wlo, &sa.w1cat_lo, err);
 }
 
 }  // namespace
