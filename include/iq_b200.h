@@ -156,6 +156,14 @@ int iq_model_forward_coalitions(iq_model *m, const float *x_dev, int point_major
                                 int64_t workspace_bytes, void *stream);
 /* rows evaluated / (B*N) of the last iq_model_forward_coalitions call of this model (1 when nothing collapsed) */
 double iq_model_last_row_fraction(const iq_model *m);
+/* Host half of iq_model_forward_coalitions, exported for tests (HOST pointers, no device work): from the kept-point counts
+ * kept[b] of B clouds of N points (N a multiple of 128) and the number of copies of the masking location a cloud must keep
+ * (k for DGCNN / GCNN, 1 for PointNet): the clouds ordered by compacted size, largest first -- src[s] = cloud at sorted
+ * position s, size[s] = its compacted number of points, extra[s] = weight the average pool owes its last point beyond 1,
+ * count[t] (t = 0 .. N/128) = clouds evaluated at 128*t points. */
+int iq_collapse_plan(const int32_t *kept, int64_t B, int64_t N, int copies, int32_t *src, int32_t *size, float *extra,
+                     int64_t *count);
+
 /* how the last forward of this model was evaluated: counts[t-1] = clouds run at 128*t points (a plain forward has all
  * its clouds in the last entry).  Fills up to `cap` entries, returns the number of entries (ceil(N/128)); bench.py
  * derives the work each kernel really did from it. */

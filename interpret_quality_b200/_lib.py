@@ -41,6 +41,7 @@ SIGNATURES = {
     "iq_model_workspace_bytes": (_i64, [_vp, _i64, _i64]),
     "iq_model_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "iq_model_forward_coalitions": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "iq_collapse_plan": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "iq_model_last_row_fraction": (ctypes.c_double, [_vp]),
     "iq_model_last_buckets": (_int, [_vp, ctypes.POINTER(_i64), _int]),
     "iq_ball_query": (_int, [_vp, _vp, _i64, _i64, _i64, ctypes.c_double, _int, _vp, _vp]),

@@ -343,6 +343,16 @@ int iq_grouped_mlp_max(const float *U, const float *V, const float *b1, const in
     return rc;
 }
 
+int iq_collapse_plan(const int32_t *kept, int64_t B, int64_t N, int copies, int32_t *src, int32_t *size, float *extra,
+                     int64_t *count)
+{
+    IQ_CHECK(kept && src && size && extra && count, "iq_collapse_plan: null pointer");
+    IQ_CHECK(N >= 128 && N % 128 == 0 && copies >= 1 && B >= 0, "iq_collapse_plan: N must be a positive multiple of 128");
+    for (int64_t b = 0; b < B; ++b) IQ_CHECK(kept[b] >= 0 && kept[b] <= N, "iq_collapse_plan: kept count out of range");
+    collapse_plan(kept, B, N, copies, src, size, extra, count);
+    return 0;
+}
+
 int iq_model_set_engine(iq_model *m, int engine)
 {
     IQ_CHECK(m && (engine == 0 || engine == 1), "iq_model_set_engine: bad argument");

@@ -113,6 +113,10 @@ Model *create_pointnet_model(const StateDict &sd, int num_classes, std::string &
 Model *create_pointnet2_model(const StateDict &sd, int num_classes, std::string &err);
 Model *create_pointconv_model(const StateDict &sd, int num_classes, std::string &err);
 
+// host half of the collapsed forward (models_common.cu), exported as iq_collapse_plan for CPU tests
+void collapse_plan(const int32_t *kept, int64_t B, int64_t N, int copies, int32_t *src, int32_t *size, float *extra,
+                   int64_t *count);
+
 // host-side folding helpers (models_common.cu)
 bool fold_dense(const StateDict &sd, const std::string &w_key, const std::string &b_key, const std::string &bn_prefix,
                 int cout, int cin, std::vector<float> &w, std::vector<float> &b, std::string &err);

@@ -285,6 +285,31 @@ int Model::plan(Workspace &ws, const float *x, int point_major, int64_t B, int64
     return 0;
 }
 
+// Host half of the collapsed forward: from the kept-point counts U[b] of B clouds of N points, the compacted size of every
+// cloud, n = N when nothing is masked, else round_up(U + min(M, copies), 128) with M = N - U (never more than N: U + M = N is
+// a multiple of 128), the clouds ordered by size, largest first (stable: original order inside a size), and the weight the
+// average pool still owes the last copy, extra = M - (n - U).  count[t] = clouds of size 128 * t.
+void collapse_plan(const int32_t *kept, int64_t B, int64_t N, int copies, int32_t *src, int32_t *size, float *extra,
+                   int64_t *count)
+{
+    const int nb = (int)(N / 128);
+    auto size_of = [&](int32_t U) -> int64_t {
+        const int64_t M = N - U;
+        return M <= 0 ? N : std::min<int64_t>(N, round_up(U + std::min<int64_t>(M, copies), 128));
+    };
+    for (int t = 0; t <= nb; ++t) count[t] = 0;
+    for (int64_t b = 0; b < B; ++b) count[size_of(kept[b]) / 128] += 1;
+    std::vector<int64_t> fill(nb + 2, 0);
+    for (int t = nb; t >= 1; --t) fill[t - 1] = fill[t] + count[t];
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t n = size_of(kept[b]);
+        const int64_t s = fill[n / 128]++;
+        src[s] = (int32_t)b;
+        size[s] = (int32_t)n;
+        extra[s] = (float)((N - kept[b]) - (n - kept[b]));                // M - m: copies not materialised
+    }
+}
+
 // The collapsed forward (collapse.cu): count the kept points per cloud, group the clouds by compacted size, rewrite
 // them, run every group through run_body at its own number of points, the head over all clouds, and hand the logits
 // back in the caller's order.  One host round trip (the kept counts) decides the grouping.
@@ -325,20 +350,8 @@ int Model::plan_collapsed(Workspace &ws, const float *x, int point_major, int64_
     // counting sort by compacted size, largest first
     const int nb = (int)(N / 128);
     std::vector<int64_t> count(nb + 1, 0), start(nb + 2, 0);
-    auto size_of = [&](int32_t U) -> int64_t {
-        const int64_t M = N - U;
-        return M <= 0 ? N : std::min<int64_t>(N, round_up(U + std::min<int64_t>(M, copies), 128));
-    };
-    for (int64_t b = 0; b < B; ++b) count[size_of(h_kept[b]) / 128] += 1;
+    collapse_plan(h_kept, B, N, copies, h_src, h_size, h_extra, count.data());
     for (int t = nb; t >= 1; --t) start[t - 1] = start[t] + count[t];     // start[t] = first sorted position of size 128*t
-    std::vector<int64_t> fill(start.begin(), start.end());
-    for (int64_t b = 0; b < B; ++b) {
-        const int64_t n = size_of(h_kept[b]);
-        const int64_t s = fill[n / 128]++;
-        h_src[s] = (int32_t)b;
-        h_size[s] = (int32_t)n;
-        h_extra[s] = (float)((N - h_kept[b]) - (n - h_kept[b]));            // M - m: copies not materialised
-    }
     int64_t rows = 0;
     for (int64_t s = 0; s < B; ++s) { h_off[s] = (int32_t)rows; rows += h_size[s]; }
     last_row_fraction = (double)rows / (double)(B * N);
