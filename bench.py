@@ -353,6 +353,8 @@ def kernel_work(model, k, buckets):
         w["tc_sa_mlp2"] = T(mac((16384, 64, 64), (8192, 128, 128), (128, 256, 512)))
         w["tc_sa_mlp3"] = T(mac((16384, 64, 128), (8192, 128, 256), (128, 512, 1024)))
         w["tc_sa_linear"] = T(mac((512, 2048, 128), (128, 4096, 256)))
+        w["tc_sa_point"] = T(mac((512, 132, 128), (128, 260, 256)))
+        w["tc_sa3_linear"] = T(mac((1, 16384, 1024)))
     return w
 
 

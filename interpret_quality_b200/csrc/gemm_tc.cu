@@ -484,7 +484,9 @@ static int pick_bn(int n)
 bool tc_gemm_supported(const TcGemm &g)
 {
     if (g.K < 4 || g.K % 4 != 0) return false;
-    if (g.mode == 0) return g.M % TBM == 0 && pick_bn(g.N) != 0;
+    // STORE: a ragged last row tile is fine for plain operands (TMA zero-fills the A rows beyond M and clips the stores);
+    // the gathered-A and the batched-Gram forms index per row and need whole tiles
+    if (g.mode == 0) return g.M >= 1 && pick_bn(g.N) != 0 && (g.M % TBM == 0 || (!g.gather.U && g.rows_per_batch == 0));
     if (g.cout < 1 || g.points < 1 || g.clouds < 1) return false;
     if (g.points >= 128) return g.points % 128 == 0;
     return 128 % g.points == 0 && ((int64_t)g.clouds * g.points) % 128 == 0;
@@ -538,7 +540,7 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
     if (g.mode == 0) {
         bn = pick_bn(g.N);
         p.n_tiles = g.N / bn; p.rows_per_batch = g.rows_per_batch; p.out_c = g.C != nullptr; p.out_hilo = g.C_hi != nullptr;
-        p.num_units = (g.M / TBM) * p.n_tiles; p.tiles_per_unit = 1;
+        p.num_units = (int)ceil_div(g.M, TBM) * p.n_tiles; p.tiles_per_unit = 1;
         a_rows = g.M;
         b_rows = g.rows_per_batch > 0 ? g.M : g.N;
         IQ_CHECK((g.C || (g.C_hi && g.C_lo)) && g.ldc % 4 == 0, "gemm_tc: no output or misaligned leading dimension");

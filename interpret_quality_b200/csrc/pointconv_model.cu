@@ -231,6 +231,7 @@ struct SaLayer {
     double bandwidth = 0;
     bool group_all = false;
     float *w1 = nullptr;          // (c1, ldw) over our point-feature rows [features ; xyz ; pad] (reference order is xyz first)
+    float *w1_hi = nullptr, *w1_lo = nullptr;   // its tf32 split (tcgen05 path of the per-point product)
     float *w1x = nullptr;         // (c1, 3)
     float *b1 = nullptr;
     Dense l2, l3, lin;            // lin: Linear(16*c3 -> c3) + bn_linear
@@ -263,6 +264,10 @@ protected:
         IQ_CHECK(ws.ok(), "pointconv: workspace too small");
         if (ws.dry) return 0;
         const Dense &lin = sa[2].lin;
+        // Linear(16 * 1024 -> 1024) + BN + ReLU of the group-all layer stays on the fp32 SIMT GEMM.  Measured on tcgen05
+        // (gemm_tc STORE, K = 16384): the logits sit 1.1e-4 of scale from float64 with 3 and with 4 split terms alike -- so it is
+        // the length of the TMEM accumulation, not the operand split -- against 2e-5 for the FMA chain; the 10 ms per 5440
+        // clouds it would save are not worth leaving the fp32-noise band the tests hold every model to.
         if (int rc = sgemm(agg3, 16384, lin.w, 16384, lin.b, f1024, 1024, B, 1024, 16384, ACT_RELU, "sgemm_sa3_linear", st))
             return rc;
         if (int rc = sgemm(f1024, 1024, fc1.w, 1024, fc1.b, f512, 512, B, 512, 1024, ACT_RELU, "sgemm_head", st)) return rc;
@@ -300,7 +305,17 @@ protected:
             if (int rc = launch_fps(src_xyz, Bc, Nsrc, S, nullptr, nullptr, new_xyz, st)) return rc;
             if (int rc = launch_knn_point(src_xyz, new_xyz, Bc, Nsrc, S, K, s.idx, st)) return rc;
         }
-        if (int rc = sgemm(src_in, ld_in, L.w1, L.ldw, nullptr, s.U, L.c1, Bc * Nsrc, L.c1, kin, ACT_NONE, "sgemm_sa_point", st))
+        // U = [features ; xyz] W1^T per source point: K = 3 in sa1 (SIMT), 132 / 260 in sa2 / sa3 -> tcgen05 on the tf32 split
+        // of the source rows (written into the grouped-activation scratch, idle at this point)
+        TcGemm pt;
+        pt.A_hi = s.h1hi; pt.A_lo = s.h1lo; pt.lda = ld_in; pt.B_hi = L.w1_hi; pt.B_lo = L.w1_lo; pt.ldb = L.ldw; pt.K = kin;
+        pt.M = (int)(Bc * Nsrc); pt.N = L.c1; pt.C = s.U; pt.ldc = L.c1; pt.tag = "tc_sa_point";
+        pt.four_terms = 1;           // U - V cancels downstream (relu(U[idx] - V + b1)): keep the Alo*Blo term, fp32-chain accuracy
+        if (engine == 1 && kin >= 32 && s.h1lo && tc_gemm_supported(pt)) {
+            if (int rc = launch_split_tf32(src_in, Bc * Nsrc, kin, ld_in, s.h1hi, s.h1lo, ld_in, st)) return rc;
+            if (int rc = launch_gemm_tc(pt, st)) return rc;
+        } else if (int rc = sgemm(src_in, ld_in, L.w1, L.ldw, nullptr, s.U, L.c1, Bc * Nsrc, L.c1, kin, ACT_NONE,
+                                  "sgemm_sa_point", st))
             return rc;
         if (int rc = sgemm(new_xyz, 3, L.w1x, 3, nullptr, s.V, L.c1, cents, L.c1, 3, ACT_NONE, "sgemm_sa_centroid", st))
             return rc;
@@ -454,7 +469,11 @@ bool make_sa(PointConvModel *m, const StateDict &sd, const std::string &p, int n
             w1x[(size_t)o * 3 + i] = w[(size_t)o * cin + i];
         }
     }
-    if (!(up(m, w1, &L.w1, err) && up(m, w1x, &L.w1x, err) && up(m, b, &L.b1, err))) return false;
+    std::vector<float> w1hi, w1lo;
+    split_tf32_host(w1, w1hi, w1lo);
+    if (!(up(m, w1, &L.w1, err) && up(m, w1x, &L.w1x, err) && up(m, b, &L.b1, err) && up(m, w1hi, &L.w1_hi, err) &&
+          up(m, w1lo, &L.w1_lo, err)))
+        return false;
     if (!make_dense(m, sd, p + ".mlp_convs.1", p + ".mlp_bns.1", L.c2, L.c1, L.l2, err)) return false;
     if (!make_dense(m, sd, p + ".mlp_convs.2", p + ".mlp_bns.2", L.c3, L.c2, L.l3, err)) return false;
     if (!make_dense(m, sd, p + ".linear", p + ".bn_linear", L.c3, 16 * L.c3, L.lin, err)) return false;

@@ -79,6 +79,7 @@ protected:
         TcGemm pt;
         pt.A_hi = h1hi; pt.A_lo = h1lo; pt.lda = ld_in; pt.B_hi = sa.w1cat_hi; pt.B_lo = sa.w1cat_lo; pt.ldb = sa.ldw;
         pt.K = kin; pt.M = (int)(Bc * Nsrc); pt.N = sa.c1_total; pt.C = U; pt.ldc = sa.c1_total; pt.tag = "tc_sa_point";
+        pt.four_terms = 1;           // U - V cancels downstream (relu(U[idx] - V + b1)): keep the Alo*Blo term, fp32-chain accuracy
         if (engine == 1 && kin >= 32 && h1lo && tc_gemm_supported(pt)) {
             if (int rc = launch_split_tf32(src_in, Bc * Nsrc, kin, ld_in, h1hi, h1lo, ld_in, st)) return rc;
             if (int rc = launch_gemm_tc(pt, st)) return rc;

@@ -14,9 +14,12 @@ def cu(a):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 64), (256, 128, 128), (1024, 256, 64), (4096, 512, 128),
-                                   (2048, 1024, 512), (128 * 149, 128, 96)])
+                                   (2048, 1024, 512), (128 * 149, 128, 96), (1, 128, 64), (200, 256, 260), (5440, 1024, 2048),
+                                   (128 * 3 + 127, 320, 132)])
 @pytest.mark.parametrize("act", [0, 2])
 def test_store_epilogue_vs_float64(M, N, K, act):
+    """Includes row counts that are not multiples of 128 (TMA zero-fills the ragged A tile and clips the stores) and K
+    that is not a multiple of 32 (zero-filled K tail): the shapes of the classifier heads and the per-point products."""
     rs = np.random.RandomState(M + N + K)
     x = (rs.normal(size=(M, K)) * rs.uniform(0.1, 4.0, size=(1, K))).astype(np.float32)
     w = rs.normal(size=(N, K)).astype(np.float32)
@@ -30,7 +33,9 @@ def test_store_epilogue_vs_float64(M, N, K, act):
     scale = np.abs(want).max()
     e_tc, e_fp32 = np.abs(got_tc - want).max() / scale, np.abs(got_fp32 - want).max() / scale
     assert e_fp32 <= 2e-6
-    assert e_tc <= 1e-5, (e_tc, e_fp32)            # 3xTF32 sits at fp32 noise; single-pass TF32 would be ~5e-4
+    # 3xTF32 sits at fp32 noise; single-pass TF32 would be ~5e-4.  The dropped Alo*Blo terms add up with sqrt(K):
+    # 1.4e-5 at K = 2048 (products that long keep the fourth term in the models: TcGemm::four_terms)
+    assert e_tc <= (1e-5 if K <= 512 else 2e-5), (e_tc, e_fp32)
 
 
 def test_single_pass_tf32_would_fail_this_bar():
