@@ -37,7 +37,7 @@ protected:
     int pooled_dim() const override { return 2048; }
     // A k-nearest-neighbour list sees at most k of the coincident copies (collapse.cu); the average pool carries the
     // rest as a weight, which only the tcgen05 pooling epilogue implements.
-    int collapse_copies() const override { return engine == 1 ? k : -1; }
+    int collapse_copies() const override { return engine == 1 ? k : -1; }   // (forward() only collapses when N % 128 == 0)
 
     int run_head(Workspace &ws, const float *g, int64_t B, float *logits, cudaStream_t st) override
     {
@@ -61,13 +61,16 @@ protected:
     int run_body(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *g, float *,
                  int64_t *, cudaStream_t st) override
     {
-        IQ_CHECK(N % 128 == 0, "dgcnn/gcnn: num_points must be a multiple of 128");
         IQ_CHECK(N <= 2048, "dgcnn/gcnn: num_points must be <= 2048");
         IQ_CHECK(k <= N, "dgcnn/gcnn: k exceeds num_points");
+        // The tensor-core kernels tile a cloud in 128-point blocks.  Any other number of points (the reference takes N from
+        // the tensor's shape, models/dgcnn.py:12-18) runs the exact fp32 route: SIMT Gram + exact top-k, SIMT products, the
+        // generic gather, and conv5 written out and pooled row by row -- the same results as the fp32 engine, at its speed.
+        const bool aligned = N % 128 == 0;
         const int64_t rows = Bc * N;
         float *xyz = ws.take<float>(rows * 3);
         int32_t *idx = ws.take<int32_t>(rows * k);
-        const bool tc = engine == 1;
+        const bool tc = engine == 1 && aligned;
         // feature-space kNN fused on tcgen05 (knn_tc.cu): the N x N key matrix is never written
         const bool tc_knn = dynamic && tc && knn_features_tc_supported(N, 64, k) && knn_features_tc_supported(N, 128, k);
         uint32_t *cand = tc_knn ? ws.take<uint32_t>(rows * 2 * (N / 32)) : nullptr;
@@ -79,8 +82,9 @@ protected:
         float *feat_lo = tc ? ws.take<float>(rows * 512) : nullptr;
         float *dist = (dynamic && !tc_knn) ? ws.take<float>(Bc * N * N) : nullptr;
         const int tiles = (int)(N / 128);
-        float *pmax = ws.take<float>(Bc * tiles * 1024);
-        float *psum = ws.take<float>(Bc * tiles * 1024);
+        float *pmax = aligned ? ws.take<float>(Bc * tiles * 1024) : nullptr;
+        float *psum = aligned ? ws.take<float>(Bc * tiles * 1024) : nullptr;
+        float *c5out = aligned ? nullptr : ws.take<float>(rows * 1024);
         IQ_CHECK(ws.ok(), "dgcnn/gcnn: workspace too small");
         if (ws.dry) return 0;
 
@@ -148,7 +152,13 @@ protected:
         }
         GemmDesc c5;
         c5.A = feat; c5.lda = 512; c5.B = conv5.w; c5.ldb = 512; c5.M = (int)rows; c5.N = 1024; c5.K = 512;
-        c5.bias = conv5.b; c5.act = ACT_LRELU; c5.pool_max = pmax; c5.pool_sum = psum; c5.tag = "sgemm_conv5_pool";
+        c5.bias = conv5.b; c5.act = ACT_LRELU; c5.tag = "sgemm_conv5_pool";
+        if (!aligned) {                                  // (B, N, 1024) written once, max / mean over each cloud's N rows
+            c5.C = c5out; c5.ldc = 1024;
+            if (int rc = launch_sgemm(c5, st)) return rc;
+            return launch_pool_finish(c5out, nullptr, c5out, Bc, (int)N, (int)N, 1024, g, 2048, nullptr, g + 1024, 2048, st);
+        }
+        c5.pool_max = pmax; c5.pool_sum = psum;
         if (int rc = launch_sgemm(c5, st)) return rc;
         if (int rc = launch_pool_finish(pmax, nullptr, psum, Bc, tiles, (int)N, 1024, g, 2048, nullptr, g + 1024, 2048, st))
             return rc;

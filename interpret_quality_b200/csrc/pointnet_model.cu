@@ -30,6 +30,23 @@ struct TNet {
     int k = 3;
 };
 
+// (B, Nin, 3) or (B, 3, Nin) -> point-major (B, Npad, 3); rows >= Nin repeat the cloud's first point
+__global__ void pad_cloud_kernel(const float *__restrict__ x, int point_major, int Nin, int Npad, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (i >= Npad) return;
+    const int j = i < Nin ? i : 0;
+    float *o = out + (b * Npad + i) * 3;
+    if (point_major) {
+        const float *p = x + (b * Nin + j) * 3;
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    } else {
+        const float *p = x + b * 3 * Nin + j;
+        o[0] = p[0]; o[1] = p[Nin]; o[2] = p[2 * (int64_t)Nin];
+    }
+}
+
 class PointNetModel : public Model {
 public:
     TNet stn, fstn;
@@ -126,7 +143,11 @@ protected:
     int run_body(Workspace &ws, const float *x, int point_major, int64_t Bc, int64_t N, float *pooled,
                  float *aux_trans_feat, int64_t *aux_crt, cudaStream_t st) override
     {
-        IQ_CHECK(N % 128 == 0, "pointnet: num_points must be a multiple of 128");
+        // The pooled GEMMs tile a cloud in 128-point blocks.  PointNet only ever takes the max over the points, so any other
+        // number of points is padded with copies of each cloud's first point: the pooled maxima and -- ties go to the lowest
+        // index -- the critical-point indices are those of the unpadded cloud (models/pointnet.py:77-88 takes N from the shape).
+        const int64_t Nin = N;
+        N = round_up(N, 128);
         const int64_t rows = Bc * N;
         const int tiles = (int)(N / 128);
         float *xyz = ws.take<float>(rows * 3);
@@ -151,7 +172,12 @@ protected:
         if (ws.dry) return 0;
 
         const float *pts = x;
-        if (!point_major) {
+        if (Nin != N) {
+            pad_cloud_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)Bc), 256, 0, st>>>(x, point_major, (int)Nin, (int)N, xyz);
+            IQ_COUNT_LAUNCH();
+            IQ_LAUNCH_CHECK();
+            pts = xyz;
+        } else if (!point_major) {
             if (int rc = launch_xyz_to_point_major(x, Bc, N, xyz, st)) return rc;
             pts = xyz;
         }

@@ -199,3 +199,33 @@ def test_lanes_do_not_change_the_result(name):
         assert torch.equal(got, want) and torch.isfinite(total)
     with pytest.raises(Exception):
         model.set_lanes(5)
+
+
+@pytest.mark.parametrize("name,N", [("dgcnn", 1000), ("dgcnn", 200), ("gcnn", 1000), ("pointnet", 1000), ("pointnet", 77)])
+def test_any_number_of_points(name, N):
+    """The reference takes N from the tensor's shape (models/dgcnn.py:12-18, models/pointnet.py:77-88); the tensor-core
+    kernels tile clouds in 128-point blocks.  Other N run the exact fp32 route (DGCNN / GCNN) or are padded with copies of
+    the first point (PointNet: max pools only) -- against the oracle on masked and unmasked clouds, with and without the
+    coalition hint, and PointNet's critical-point indices against the oracle's."""
+    from oracle import geom, nets
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True, device=DEV)
+    sd = synthetic.make_state_dict(name)
+    model = final_util.build_model(a, sd)
+    data = synthetic.make_cloud(N)
+    regions = 8
+    rid = geom.region_id(data[0], geom.fps(data, regions)[0])
+    center = coalition.center_of(data)
+    masked = geom.mask_shapley(data[0], center, synthetic.make_orders(1, regions), rid)          # (9, N, 3)
+    x = torch.from_numpy(masked).permute(0, 2, 1).contiguous()
+    want = nets.forward(name, x, sd).numpy()
+    got = model(x.to(DEV))
+    got_l = (got[0] if isinstance(got, tuple) else got).cpu().numpy()
+    scale = np.abs(want).max()
+    err = np.abs(got_l - want).max(1) / scale
+    print("%s N=%d: per-cloud error vs oracle max %.2e median %.2e" % (name, N, err.max(), np.median(err)))
+    assert np.median(err) <= 1e-5 and err.max() <= 1e-3
+    hinted = model.forward_point_major(torch.from_numpy(masked).to(DEV), masked_to=torch.from_numpy(center).to(DEV))
+    assert np.array_equal(hinted.cpu().numpy(), got_l)                   # no collapse at this N: the plain route, bit for bit
+    if name == "pointnet":
+        want_crt = nets.pointnet(x[-1:], sd)[2].numpy()                  # the unmasked cloud: no duplicated points, no ties
+        assert (got[2][-1:].cpu().numpy() == want_crt).mean() > 0.99
