@@ -243,8 +243,24 @@ inline EncodeTiledFn encode_fn()
 }
 
 // 2-D map over a K-major fp32 matrix (rows, K) with leading dimension ld; box = 32 x box_rows, 128B swizzle
+// The forward re-launches the same kernels on the same workspace addresses every step, so encoded maps are kept in a
+// small per-thread table keyed by everything that goes into them (cuTensorMapEncodeTiled is pure host work, but seven
+// calls per GEMM launch add up over ~100 tensor-core launches per step).
+struct MapKey {
+    const void *base; int64_t rows, ld; int K, box_rows;
+    bool operator==(const MapKey &o) const { return base == o.base && rows == o.rows && ld == o.ld && K == o.K && box_rows == o.box_rows; }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+constexpr int MAP_CACHE = 256;                                  // direct-mapped; a collision just re-encodes
+
 inline int make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int64_t ld, int box_rows)
 {
+    static thread_local MapSlot cache[MAP_CACHE] = {};
+    const MapKey key{base, rows, ld, K, box_rows};
+    uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
+    h ^= (uint64_t)rows * 0x9E3779B97F4A7C15ull + (uint64_t)ld * 0xC2B2AE3D27D4EB4Full + (uint64_t)K * 1315423911ull + (uint64_t)box_rows;
+    MapSlot &slot = cache[(h ^ (h >> 29)) % MAP_CACHE];
+    if (slot.used && slot.key == key) { *map = slot.map; return 0; }
     EncodeTiledFn fn = encode_fn();
     IQ_CHECK(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
     IQ_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0, "gemm_tc: operand must be 16-byte aligned");
@@ -256,6 +272,9 @@ inline int make_map(CUtensorMap *map, const float *base, int64_t rows, int K, in
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IQ_CHECK(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    slot.key = key;
+    slot.map = *map;
+    slot.used = true;
     return 0;
 }
 
