@@ -4,12 +4,12 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
 N=${1:-2}
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > $OUT/r2_3_bench_${N}gpu.json 2> $OUT/r2_3_bench_${N}gpu.err; echo "bench $N rc=$?"; tail -3 $OUT/r2_3_bench_${N}gpu.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/pose_shard_probe.py > $OUT/r2_3_pose_shard_${N}gpu.log 2>&1; echo "pose shard rc=$?"; tail -6 $OUT/r2_3_pose_shard_${N}gpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > $OUT/r2_f_bench_${N}gpu.json 2> $OUT/r2_f_bench_${N}gpu.err; echo "bench $N rc=$?"; tail -3 $OUT/r2_f_bench_${N}gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/pose_shard_probe.py > $OUT/r2_f_pose_shard_${N}gpu.log 2>&1; echo "pose shard rc=$?"; tail -6 $OUT/r2_f_pose_shard_${N}gpu.log
 python - <<PY
 import json
 try:
-    d = json.loads(open("gpurun_out/r2_3_bench_${N}gpu.json").read().strip().splitlines()[-1])
+    d = json.loads(open("gpurun_out/r2_f_bench_${N}gpu.json").read().strip().splitlines()[-1])
     print("n_gpus", d["n_gpus"], "value %.0f e2e %.0f ms %.2f" % (d["value"], d["e2e"]["value"], d["ms_per_step"]))
     print("strong", d["strong"])
     for k, v in (d["configs"] or {}).items():
