@@ -498,9 +498,14 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
         float d32[ITERS];
 #pragma unroll
         for (int i0 = 0; i0 < ITERS; i0 += 2) {
+            // two steps' worth of loads in flight; a step whose CPI slots lie beyond n is skipped (n is warp-uniform; about
+            // 24.5 of the 32 slots are filled on average, so the last step is empty for half of the rows)
             float4 b[2][4];
+            bool live[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
+                live[u] = (i0 + u) * CPI < n;
+                if (!live[u]) continue;
                 const int slot = (i0 + u) * CPI + grp;
                 const int j = slot < n ? (int)cl[slot] : self;
                 const float4 *xj = reinterpret_cast<const float4 *>(x + (cloud0 + j) * ld);
@@ -510,14 +515,16 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 float acc = 0.0f;
+                if (live[u]) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float d0 = xi[q].x - b[u][q].x, d1 = xi[q].y - b[u][q].y;
-                    const float d2 = xi[q].z - b[u][q].z, d3 = xi[q].w - b[u][q].w;
-                    acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+                    for (int q = 0; q < 4; ++q) {
+                        const float d0 = xi[q].x - b[u][q].x, d1 = xi[q].y - b[u][q].y;
+                        const float d2 = xi[q].z - b[u][q].z, d3 = xi[q].w - b[u][q].w;
+                        acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+                    }
+#pragma unroll
+                    for (int o = LPC / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
                 }
-#pragma unroll
-                for (int o = LPC / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
                 d32[i0 + u] = acc;
             }
         }
