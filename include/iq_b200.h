@@ -182,8 +182,8 @@ int iq_ball_query(const float *xyz_dev, const float *new_xyz_dev, int64_t B, int
 int iq_knn_xyz(const float *xyz_dev, int64_t B, int64_t N, int k, int32_t *idx_dev, void *stream);
 
 /* knn(x, k) on features: models/dgcnn.py:12-18 as used by DGCNN_cls.forward :94-104.  x (B*N, C) point-major,
- * C in {64,128}, N a multiple of 128, k <= 20 -> idx (B,N,k) i32, the k nearest points of the same cloud ordered by
- * (squared distance, index); the distance is sum_c (x_i[c]-x_j[c])^2 evaluated directly.  cand_count_dev (B*N) i32 or
+ * C in {64,128}, N a multiple of 128, k <= 20 -> idx (B,N,k) i32, the SET of the k nearest points of the same cloud under
+ * (squared distance, index), in no particular order (the consumer takes a max over it); the distance is sum_c (x_i[c]-x_j[c])^2 evaluated directly.  cand_count_dev (B*N) i32 or
  * NULL receives the size of each row's candidate list (diagnostics: > 64 means the exhaustive path decided the row). */
 int iq_knn_features(const float *x_dev, int64_t B, int64_t N, int64_t C, int k, int32_t *idx_dev,
                     int32_t *cand_count_dev, void *stream);

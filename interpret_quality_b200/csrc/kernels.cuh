@@ -127,7 +127,7 @@ constexpr int KNN_CAND_CAP = 64;      // most candidates per row the re-rank han
 bool knn_features_tc_supported(int64_t N, int C, int k);
 // x (clouds*N, C) fp32 with leading dimension ld, x_hi / x_lo its tf32 split (same ld); nxx (rows, nxx_parts): the
 // squared norm of row j is |sum_p nxx[j][p]| (one negated value, or positive partial sums);
-// scratch: masks (rows, 2, N/32) u32, cnt (rows) i32; out idx (rows, k) sorted by (distance, index)
+// scratch: masks (rows, 2, N/32) u32, cnt (rows) i32; out idx (rows, k): the SET of the k nearest by (distance, index)
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
                            int nxx_parts, int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
                            cudaStream_t st);

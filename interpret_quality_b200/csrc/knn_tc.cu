@@ -534,6 +534,30 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
             const float v = __shfl_sync(FULL, d32[it], (lane % CPI) * LPC);
             if (lane / CPI == it) mine = v;
         }
+        if (n - k <= 12) {
+            // Only n - k (4.5 on average) candidates have to go: drop the largest (distance, index) that many times -- two REDUX
+            // per removal -- instead of sorting all 32 (a 15-stage network on 64-bit keys).  Distances are >= 0, so their bit
+            // patterns order like unsigned integers.  The neighbours are written in candidate (= column) order: a SET, as the
+            // max over the neighbourhood needs.
+            const uint32_t dbits = __float_as_uint(mine);
+            bool alive = lane < n;
+            const uint32_t my_col = lane < n ? (uint32_t)cl[lane] + 1u : 0u;
+            uint32_t last = 0;
+            for (int r = n - k; r > 0; --r) {
+                last = __reduce_max_sync(FULL, alive ? dbits : 0u);
+                const bool top = alive && dbits == last;
+                const uint32_t pick = __reduce_max_sync(FULL, top ? my_col : 0u);   // ties: the higher index goes first
+                if (top && my_col == pick) alive = false;
+            }
+            const float dk1 = __uint_as_float(__reduce_max_sync(FULL, alive ? dbits : 0u));   // k-th smallest
+            const float dk = __uint_as_float(last);                                           // (k+1)-th smallest, if n > k
+            const bool ambiguous = n > k && dk != dk1 && dk - dk1 <= 8e-6f * dk;
+            if (!ambiguous) {
+                const unsigned keep = __ballot_sync(FULL, alive);
+                if (alive) idx[row * k + __popc(keep & ((1u << lane) - 1u))] = (int)my_col - 1;
+                return;
+            }
+        } else {
         unsigned long long key = lane < n ? ((unsigned long long)__float_as_uint(mine) << 32) | (unsigned)cl[lane] : ~0ull;
 #pragma unroll
         for (int kk = 2; kk <= 32; kk <<= 1) {
@@ -550,6 +574,7 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
         if (!ambiguous) {
             if (lane < k) idx[row * k + lane] = (int)(key & 0xffffffffu);
             return;
+        }
         }
     }
     const int batches = n > 32 ? 2 : 1;

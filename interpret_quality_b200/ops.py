@@ -177,7 +177,7 @@ def knn_xyz(xyz, k):
 
 
 def knn_features(x, k, return_counts=False):
-    """x (B,N,C) point-major features, C in {64,128} -> (B,N,k) int32 nearest points ordered by (distance, index):
+    """x (B,N,C) point-major features, C in {64,128} -> (B,N,k) int32: the SET of the k nearest points by (distance, index), in no particular order:
     the fused tcgen05 Gram + candidate selection + exact re-rank of csrc/knn_tc.cu (models/dgcnn.py:12-18)."""
     _chk(x, torch.float32, "x")
     B, N, C = x.shape

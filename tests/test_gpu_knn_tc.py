@@ -41,16 +41,15 @@ def check(x, k, expect_exhaustive_rows=None):
     got, cnt = got.cpu().numpy(), cnt.cpu().numpy()
     want, _ = exhaustive(x, k)
     # The SET of neighbours is the float64 decision (the fp32 fast path defers to float64 whenever the k-th and
-    # (k+1)-th distances are within its error bound); the order inside the set is by the fp32 distance, which may
-    # swap two neighbours whose distances agree to ~1e-6.
+    # (k+1)-th distances are within its error bound).  The order inside the set is unspecified: the consumer takes a max
+    # over the neighbourhood, and the fast path removes the n - k farthest candidates instead of sorting them all.
     same_set = np.sort(got, -1) == np.sort(want, -1)
     if not same_set.all():
         # float64 sums in two different orders may still swap two points at the boundary when they agree to ~1e-15
         dg, dw = np.sort(dist_of(x, got), -1), np.sort(dist_of(x, want), -1)
         assert np.allclose(dg, dw, rtol=1e-12, atol=0), "neighbour set differs from the exhaustive float64 kNN"
         assert same_set.mean() > 0.9999
-    dg = dist_of(x, got)
-    assert (dg[..., 1:] >= dg[..., :-1] * (1 - 1e-5)).all(), "neighbours are not ordered by distance"
+    assert (np.sort(got, -1)[..., 1:] != np.sort(got, -1)[..., :-1]).all(), "a neighbour is listed twice"
     redo = (cnt > 64) | (cnt < k)
     if expect_exhaustive_rows is not None:
         assert bool(redo.any()) == expect_exhaustive_rows
