@@ -238,6 +238,17 @@ struct SaLayer {
     SmallNets nets;
 };
 
+// out[m][n] = relu(sum_s part[s][m][n] + bias[n]): the fixed-order reduction of a split-K product
+__global__ void splitk_reduce_kernel(const float *__restrict__ part, int S, int64_t MN, int N, const float *__restrict__ bias,
+                                     float *__restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= MN) return;
+    float acc = part[t];
+    for (int s = 1; s < S; ++s) acc += part[(int64_t)s * MN + t];
+    out[t] = fmaxf(acc + bias[t % N], 0.0f);
+}
+
 class PointConvModel : public Model {
 public:
     SaLayer sa[3];
@@ -261,9 +272,24 @@ protected:
         float *f1024 = ws.take<float>(B * 1024);
         float *f512 = ws.take<float>(B * 512);
         float *f256 = ws.take<float>(B * 256);
+        // Few clouds leave the 16384 -> 1024 Linear with ceil(B / 128) * 8 CTAs (2.8 ms for 66 clouds, ncu): split K sixteen ways
+        // over the batch dimension of the SIMT GEMM and add the partial products in a fixed order
+        constexpr int SPLIT = 16;
+        const bool splitk = B <= 1024;
+        float *part = splitk ? ws.take<float>((int64_t)SPLIT * B * 1024) : nullptr;
         IQ_CHECK(ws.ok(), "pointconv: workspace too small");
         if (ws.dry) return 0;
         const Dense &lin = sa[2].lin;
+        if (splitk) {
+            GemmDesc g;
+            g.A = agg3; g.lda = 16384; g.strideA = 16384 / SPLIT; g.B = lin.w; g.ldb = 16384; g.strideB = 16384 / SPLIT;
+            g.C = part; g.ldc = 1024; g.strideC = B * 1024; g.M = (int)B; g.N = 1024; g.K = 16384 / SPLIT; g.batch = SPLIT;
+            g.tag = "sgemm_sa3_linear";
+            if (int rc = launch_sgemm(g, st)) return rc;
+            splitk_reduce_kernel<<<(unsigned)ceil_div(B * 1024, 256), 256, 0, st>>>(part, SPLIT, B * 1024, 1024, lin.b, f1024);
+            IQ_COUNT_LAUNCH();
+            IQ_LAUNCH_CHECK();
+        } else
         // Linear(16 * 1024 -> 1024) + BN + ReLU of the group-all layer stays on the fp32 SIMT GEMM.  Measured on tcgen05
         // (gemm_tc STORE, K = 16384): the logits sit 1.1e-4 of scale from float64 with 3 and with 4 split terms alike -- so it is
         // the length of the TMEM accumulation, not the operand split -- against 2e-5 for the FMA chain; the 10 ms per 5440
