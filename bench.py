@@ -549,17 +549,17 @@ STEPS = {"shapley": shapley_steps, "interactions": interaction_steps, "sweep": s
 
 
 def quick_config(rig, name, split=None):
-    """A short measurement of one BASELINE config for the `configs` leg: 1 warm-up + 2 timed steps."""
+    """A short measurement of one BASELINE config for the `configs` leg: 3 warm-up + 3 timed steps (e2e: 1 + 2)."""
     c = dict(CONFIGS[name])
     split = split or c.get("split", "weak")
     inp = build_inputs(rig, c)
     resident, e2e, _, fw, h2d, d2h = STEPS[c["kind"]](rig, c, inp, split)
-    ms, _, _ = rig.timed(resident, 2, 1)
-    e_ms, _, _ = rig.timed(e2e, 2, 1)
-    out = {"workload": workload_name(c), "split": split, "forwards_per_step": fw, "value": fw * 2 / (ms * 1e-3),
-           "e2e": fw * 2 / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
+    ms, _, _ = rig.timed(resident, 3, 3)
+    e_ms, _, _ = rig.timed(e2e, 2, 3 if c["kind"] != "shapley" or c["perms"] <= 100 else 1)
+    out = {"workload": workload_name(c), "split": split, "forwards_per_step": fw, "value": fw * 3 / (ms * 1e-3),
+           "e2e": fw * 2 / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 3, "steps": 3, "warmup": 3,
            "rows_evaluated_fraction": inp.model.last_row_fraction(),
-           "as_written_tflops": fw * 2 / (ms * 1e-3) * MODEL_GFLOP[c["model"]] / 1e3 if c["points"] == 1024 else None}
+           "as_written_tflops": fw * 3 / (ms * 1e-3) * MODEL_GFLOP[c["model"]] / 1e3 if c["points"] == 1024 else None}
     if c["kind"] == "sweep":                                 # per batch size, inputs resident
         from interpret_quality_b200 import ops
         cen = ops.center(inp.data_dev.reshape(-1, 3))
@@ -567,7 +567,7 @@ def quick_config(rig, name, split=None):
         for B in c["batches"]:
             sub = dict(c, batches=(B,))
             r1, _, _, fw1, _, _ = sweep_steps(rig, sub, inp, split)
-            ms1, _, _ = rig.timed(r1, 3, 1)
+            ms1, _, _ = rig.timed(r1, 3, 3)
             per[str(B)] = fw1 * 3 / (ms1 * 1e-3)
         out["forwards_per_s_by_batch"] = per
         out["note"] = "one step = forwards of %s masked clouds back to back; per-batch values: 3 timed steps each" % (
@@ -611,7 +611,7 @@ def run_b200(a):
     warm = max(a.warmup, 3)
     total_ms, launches, clocks = rig.timed(resident_step, a.steps, warm, ClockSampler(rig.local))
     value = fwd_per_step * a.steps / (total_ms * 1e-3)
-    e2e_ms, _, _ = rig.timed(e2e_step, a.steps, 1)
+    e2e_ms, _, _ = rig.timed(e2e_step, a.steps, 3)
     e2e_value = fwd_per_step * a.steps / (e2e_ms * 1e-3)
     row_fraction = model.last_row_fraction()
 
@@ -695,7 +695,7 @@ def run_b200(a):
             sc = dict(c)
             sinp = build_inputs(rig, sc)
             s_res, s_e2e, _, s_fw, _, _ = shapley_steps(rig, sc, sinp, "strong")
-            s_ms, _, _ = rig.timed(s_res, a.steps, 2)
+            s_ms, _, _ = rig.timed(s_res, a.steps, 3)
             strong = {"value": s_fw * a.steps / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / a.steps,
                       "steps": a.steps, "permutations_total": sc["perms"], "forwards_per_step": s_fw,
                       "note": "the reference's fixed-size call (tools/final_common.py:64-103, num_samples = %d) with its "
