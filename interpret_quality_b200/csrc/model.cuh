@@ -78,6 +78,11 @@ public:
 private:
     cudaStream_t side_[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev_ = nullptr, join_ev_[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+    // The scratch, the lane events and the pinned staging buffer belong to the handle, so forwards of one handle are ordered
+    // even when the caller switches streams: a forward on another stream than the previous one first waits for its end.
+    cudaEvent_t done_ev_ = nullptr;
+    cudaStream_t last_stream_ = nullptr;
+    bool has_last_ = false;
     int32_t *host_meta_ = nullptr;     // pinned staging of the collapse plan (kept counts in, sorted order out)
     int64_t host_meta_cap_ = 0;
     int plan_collapsed(Workspace &ws, const float *x, int point_major, int64_t B, int64_t N, float *logits,

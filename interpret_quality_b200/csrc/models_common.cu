@@ -188,6 +188,7 @@ Model::~Model()
         if (join_ev_[i]) cudaEventDestroy(join_ev_[i]);
     }
     if (fork_ev_) cudaEventDestroy(fork_ev_);
+    if (done_ev_) cudaEventDestroy(done_ev_);
     if (host_meta_) cudaFreeHost(host_meta_);
 }
 
@@ -417,10 +418,19 @@ int Model::forward(const float *x, int point_major, int64_t B, int64_t N, float 
     last_row_fraction = 1.0;
     last_buckets.assign((size_t)ceil_div(N, 128), 0);
     last_buckets.back() = B;
+    if (has_last_ && last_stream_ != st) IQ_CUDA(cudaStreamWaitEvent(st, done_ev_, 0));   // see model.cuh: one handle, any stream
     const bool no_collapse = env_int("IQ_NO_COLLAPSE", 0) != 0;              // A/B switch for scripts and tests
+    int rc;
     if (collapse_loc && !no_collapse && collapse_copies() >= 0 && N % 128 == 0 && N >= 128 && !aux_trans_feat && !aux_crt)
-        return plan_collapsed(ws, x, point_major, B, N, logits, collapse_loc, st);
-    return plan(ws, x, point_major, B, N, logits, aux_trans_feat, aux_crt, st);
+        rc = plan_collapsed(ws, x, point_major, B, N, logits, collapse_loc, st);
+    else
+        rc = plan(ws, x, point_major, B, N, logits, aux_trans_feat, aux_crt, st);
+    if (!done_ev_ && cudaEventCreateWithFlags(&done_ev_, cudaEventDisableTiming) != cudaSuccess) done_ev_ = nullptr;
+    if (done_ev_ && cudaEventRecord(done_ev_, st) == cudaSuccess) {
+        last_stream_ = st;
+        has_last_ = true;
+    }
+    return rc;
 }
 
 }  // namespace iq

@@ -229,3 +229,26 @@ def test_any_number_of_points(name, N):
     if name == "pointnet":
         want_crt = nets.pointnet(x[-1:], sd)[2].numpy()                  # the unmasked cloud: no duplicated points, no ties
         assert (got[2][-1:].cpu().numpy() == want_crt).mean() > 0.99
+
+
+@pytest.mark.parametrize("name", ["dgcnn", "pointnet2"])
+def test_same_handle_on_two_streams_back_to_back(name):
+    """A model handle owns ONE workspace: forwards issued back to back on two different streams must not overlap on it.
+    The library orders them (an event at the end of every forward); both results must equal the serial ones."""
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", feature_transform=True, device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict(name))
+    x1 = torch.from_numpy(masked_clouds(2)[:40]).to(DEV)
+    x2 = torch.from_numpy(masked_clouds(2)[20:60]).to(DEV).contiguous()
+    center = torch.from_numpy(coalition.center_of(synthetic.make_cloud(1024))).to(DEV)
+    want1 = model.forward_point_major(x1, masked_to=center).clone()
+    want2 = model.forward_point_major(x2, masked_to=center).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(device=DEV), torch.cuda.Stream(device=DEV)
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            got1 = model.forward_point_major(x1, masked_to=center)
+        with torch.cuda.stream(s2):
+            got2 = model.forward_point_major(x2, masked_to=center)      # same handle, other stream, no host sync in between
+        s1.synchronize()
+        s2.synchronize()
+        assert torch.equal(got1, want1) and torch.equal(got2, want2)
