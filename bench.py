@@ -304,7 +304,7 @@ def traffic_table(workload):
     return t.get("kernels", {}) if t.get("workload") == workload else {}
 
 
-def kernel_work(model, k, buckets):
+def kernel_work(model, k, buckets, points=1024):
     """Algorithmic work of one step per kernel family for the roofline leg, from the clouds the
     step really evaluated: buckets = {points per evaluated cloud: clouds} (a collapsed coalition cloud has fewer
     points than the cloud it stands for, csrc/collapse.cu).  "tensor": (logical FLOPs = 2*MAC of the fp32 product the
@@ -315,7 +315,10 @@ def kernel_work(model, k, buckets):
     sq = float(sum(n * n * c for n, c in buckets.items()))
     T = lambda flops, mult=3: ("tensor", flops, mult)
     H = lambda nbytes: ("hbm", nbytes, 1)
-    w = {"reward": H(44.0 * clouds), "shapley_accumulate": H((4.0 + 8.0 * R / (R + 1)) * clouds)}
+    w = {"reward": H(44.0 * clouds), "shapley_accumulate": H((4.0 + 8.0 * R / (R + 1)) * clouds),
+         # coalition expansion at the full cloud size, then the collapse: count reads it, compact reads it and writes the rows kept
+         "mask_shapley": H(12.0 * points * clouds), "collapse_count": H(12.0 * points * clouds),
+         "collapse_compact": H(12.0 * points * clouds + 12.0 * rows)}
     if model in ("dgcnn", "gcnn"):
         w["tc_conv5_pool"] = T(2.0 * rows * 512 * 1024)
         w["sgemm_conv5_pool"] = T(2.0 * rows * 512 * 1024, 1)
@@ -635,7 +638,7 @@ def run_b200(a):
         breakdown["by_kernel"] = {k: {"ms": round(ms, 3), "launches": n, "share": round(ms / tot, 4)} for k, (ms, n) in
                                   sorted(rep.items(), key=lambda kv: -kv[1][0])}
         if c["kind"] == "shapley":                            # one forward call per profiled step: the buckets describe it
-            work = kernel_work(c["model"], 20, buckets)
+            work = kernel_work(c["model"], 20, buckets, c["points"])
             traffic = traffic_table(workload_name(c))
             kernels = []
             for name, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
