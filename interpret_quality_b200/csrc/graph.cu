@@ -424,18 +424,29 @@ gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t
     __syncthreads();
     const int g = lane >> 3, q = lane & 7;                          // 4 points per warp instruction, 8 lanes each
     const int per = N / psplit;
-    for (int p0 = ps * per + warp * 4; p0 < (ps + 1) * per; p0 += GMS_THREADS / 8) {
+    const int p_end = (ps + 1) * per;
+    // k = 20: the neighbour list of a point is five 16-byte words.  Each of the first five lanes of the point's group loads
+    // ONE of them -- for the NEXT point the group will work on, a whole iteration ahead of its use (ncu: a third of all stall
+    // samples sat on the first use of these indices, long scoreboard) -- and the group shares them by shuffle.
+    auto load_nb = [&](int p0) -> int4 {
+        const int32_t *row = idx + (cloud0 + p0 + g) * k;
+        return q < 5 ? __ldg(reinterpret_cast<const int4 *>(row) + q) : make_int4(0, 0, 0, 0);
+    };
+    int4 nb_next = make_int4(0, 0, 0, 0);
+    if (k == 20 && ps * per + warp * 4 < p_end) nb_next = load_nb(ps * per + warp * 4);
+    for (int p0 = ps * per + warp * 4; p0 < p_end; p0 += GMS_THREADS / 8) {
         const int i = p0 + g;
         const int32_t *row = idx + (cloud0 + i) * k;
         const float4 qv = *reinterpret_cast<const float4 *>(PQ + (cloud0 + i) * ldpq + Cout + sl * 32 + q * 4);   // in flight early
         float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (k == 20) {                                              // the whole neighbour list in five 16-byte loads
-            int4 nb[5];
-#pragma unroll
-            for (int t = 0; t < 5; ++t) nb[t] = __ldg(reinterpret_cast<const int4 *>(row) + t);
+        if (k == 20) {
+            const int4 nb = nb_next;
+            if (p0 + GMS_THREADS / 8 < p_end) nb_next = load_nb(p0 + GMS_THREADS / 8);
+            const int lead = lane & ~7;
 #pragma unroll
             for (int t = 0; t < 5; ++t) {
-                const int js[4] = {nb[t].x, nb[t].y, nb[t].z, nb[t].w};
+                const int js[4] = {__shfl_sync(FULL, nb.x, lead + t), __shfl_sync(FULL, nb.y, lead + t),
+                                   __shfl_sync(FULL, nb.z, lead + t), __shfl_sync(FULL, nb.w, lead + t)};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float4 v = ptab[js[e] * 8 + q];

@@ -460,6 +460,9 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
 #pragma unroll
     for (int q = 0; q < 4; ++q) xi[q] = __ldg(reinterpret_cast<const float4 *>(x + row * ld) + q * LPC + sub);
 
+    // the first 32 words of the tie mask travel together with the first words of the "above" mask: 62 % of the rows need
+    // them, and loaded on demand they cost a second L2 round trip on the critical path (ncu: long-scoreboard stalls)
+    const uint32_t me_first = lane < words ? __ldg(me + lane) : 0u;
     int n = 0;
     for (int w0 = 0; w0 < words; w0 += 32) {                          // every column above the threshold
         const int w = w0 + lane;
@@ -476,7 +479,7 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
     }
     int need = KNN_NOM - n;                                            // then the lowest-index ties, up to NOM in all
     for (int w0 = 0; w0 < words && need > 0; w0 += 32) {
-        const uint32_t m = w0 + lane < words ? __ldg(me + w0 + lane) : 0u;
+        const uint32_t m = w0 == 0 ? me_first : (w0 + lane < words ? __ldg(me + w0 + lane) : 0u);
         const int incl = warp_inclusive_scan(__popc(m), lane);
         const int took = min(__shfl_sync(FULL, incl, 31), need);
         const int col = column_of_slot(m, incl, lane, w0);
