@@ -294,17 +294,23 @@ def measure_tf32_peak(dev):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def traffic_table(workload):
+def traffic_table(workload, f16=0):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) from the
     committed ncu --set full capture profiles/r2_traffic.json; only quoted for the workload it was captured on."""
     fn = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(fn):
         return {}
     t = json.load(open(fn))
-    return t.get("kernels", {}) if t.get("workload") == workload else {}
+    if t.get("workload") != workload:
+        return {}
+    kernels = dict(t.get("kernels", {}))
+    if t.get("f16_paths", 0) != f16:                         # captured with other operand formats: not this run's bytes
+        for stale in ("tc_conv5_pool", "gather_max", "tc_edge_pq", "tc_gram_knn_c64", "tc_gram_knn_c128"):
+            kernels.pop(stale, None)
+    return kernels
 
 
-def kernel_work(model, k, buckets, points=1024):
+def kernel_work(model, k, buckets, points=1024, f16=0):
     """Algorithmic work of one step per kernel family for the roofline leg, from the clouds the
     step really evaluated: buckets = {points per evaluated cloud: clouds} (a collapsed coalition cloud has fewer
     points than the cloud it stands for, csrc/collapse.cu).  "tensor": (logical FLOPs = 2*MAC of the fp32 product the
@@ -313,30 +319,38 @@ def kernel_work(model, k, buckets, points=1024):
     clouds = float(sum(buckets.values()))
     rows = float(sum(n * c for n, c in buckets.items()))
     sq = float(sum(n * n * c for n, c in buckets.items()))
-    T = lambda flops, mult=3: ("tensor", flops, mult)
-    H = lambda nbytes: ("hbm", nbytes, 1)
+    T = lambda flops, mult=3, kind="tf32": ("tensor", flops, mult, kind)
+    H = lambda nbytes: ("hbm", nbytes, 1, None)
+    f16_conv5, f16_store, f16_gram = bool(f16 & 1), bool(f16 & 2), bool(f16 & 4)   # csrc/edgeconv_model.cu, iq_f16_paths()
     w = {"reward": H(44.0 * clouds), "shapley_accumulate": H((4.0 + 8.0 * R / (R + 1)) * clouds),
          # coalition expansion at the full cloud size, then the collapse: count reads it, compact reads it and writes the rows kept
          "mask_shapley": H(12.0 * points * clouds), "collapse_count": H(12.0 * points * clouds),
          "collapse_compact": H(12.0 * points * clouds + 12.0 * rows)}
     if model in ("dgcnn", "gcnn"):
-        w["tc_conv5_pool"] = T(2.0 * rows * 512 * 1024)
+        w["tc_conv5_pool"] = T(2.0 * rows * 512 * 1024, 3, "f16" if f16_conv5 else "tf32")
         w["sgemm_conv5_pool"] = T(2.0 * rows * 512 * 1024, 1)
         couts = (64, 64, 128, 256)
         if model == "dgcnn":
             w["sgemm_edge_pq"] = T(2.0 * rows * (3 * 128 + 64 * 128 + 64 * 256), 1)
-            w["tc_edge_pq"] = T(2.0 * rows * 128 * 512)
+            w["tc_edge_pq"] = T(2.0 * rows * 128 * 512, 3, "f16" if f16_store else "tf32")
             w["sgemm_gram"] = T(2.0 * sq * (64 + 64 + 128), 1)
-            w["tc_gram_knn_c64"] = T(2.0 * sq * 64 * 2, 6)                    # two layers with 64-wide features
-            w["tc_gram_knn_c128"] = T(2.0 * sq * 128, 6)
+            w["tc_gram_knn_c64"] = T(2.0 * sq * 64 * 2, 6, "f16" if f16_gram else "tf32")   # two layers with 64-wide features
+            w["tc_gram_knn_c128"] = T(2.0 * sq * 128, 6, "f16" if f16_gram else "tf32")
             w["topk_rows"] = H(3.0 * (4.0 * sq + 4.0 * rows * k))
             # masks (2 bits per column pair) + the feature rows once + neighbour lists, three layers
             w["knn_rerank"] = H(3.0 * (sq / 4.0 + 4.0 * rows * k) + 4.0 * rows * (64 + 64 + 128))
         else:
             w["sgemm_edge_pq"] = T(2.0 * rows * 3 * 128, 1)
-            w["tc_edge_pq"] = T(2.0 * rows * (64 * 128 + 64 * 256 + 128 * 512))
-        # P|Q rows read once, neighbour lists, fp32 output + its tf32 hi/lo split + the squared norm
-        w["gather_max"] = H(sum(4.0 * rows * 2 * c + 4.0 * rows * k + 3 * 4.0 * rows * c + 4.0 * rows for c in couts))
+            w["tc_edge_pq"] = T(2.0 * rows * (64 * 128 + 64 * 256 + 128 * 512), 3, "f16" if f16_store else "tf32")
+        # P|Q rows read once, neighbour lists, the squared norm, and the output in the formats its consumers read
+        # (edgeconv_model.cu): fp32 (SIMT products + exact re-rank: DGCNN layers 1-3), the tf32 pair (Gram kNN and tf32
+        # tcgen05 products), the fp16 pair (kind::f16 products)
+        out_bytes = []
+        for l, c in enumerate(couts):
+            f32 = 4.0 if (model == "dgcnn" and l < 3) else 0.0
+            tf32 = 8.0 if (not f16_conv5 or (l < 3 and ((model == "dgcnn" and not f16_gram) or not f16_store))) else 0.0
+            out_bytes.append((f32 + tf32 + (4.0 if f16_conv5 else 0.0)) * rows * c)
+        w["gather_max"] = H(sum(4.0 * rows * 2 * c + 4.0 * rows * k + 4.0 * rows for c in couts) + sum(out_bytes))
         w["knn_xyz"] = H(12.0 * rows + 4.0 * rows * k)
     elif model == "pointnet":
         w["tc_conv_pool"] = T(2.0 * rows * 128 * 1024 * 3)
@@ -638,13 +652,13 @@ def run_b200(a):
         breakdown["by_kernel"] = {k: {"ms": round(ms, 3), "launches": n, "share": round(ms / tot, 4)} for k, (ms, n) in
                                   sorted(rep.items(), key=lambda kv: -kv[1][0])}
         if c["kind"] == "shapley":                            # one forward call per profiled step: the buckets describe it
-            work = kernel_work(c["model"], 20, buckets, c["points"])
-            traffic = traffic_table(workload_name(c))
+            work = kernel_work(c["model"], 20, buckets, c["points"], rig.lib.f16_paths())
+            traffic = traffic_table(workload_name(c), rig.lib.f16_paths())
             kernels = []
             for name, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
                 if name not in work:
                     continue
-                bound, per_step, mult = work[name]
+                bound, per_step, mult, mma_kind = work[name]
                 per_launch = per_step / n
                 dur = ms * 1e-3 / n
                 if bound == "tensor":
@@ -662,10 +676,16 @@ def run_b200(a):
                     # the kernels compute fp32 products as `mult` tf32 MMAs each: the executed rate is what the tensor
                     # pipe sees, against the dense TF32 rate measured at the start of this leg
                     k["mmas_per_logical_mac"] = mult
+                    k["mma_kind"] = mma_kind
                     k["executed_tflops"] = ach * mult
-                    # cuBLAS dense TF32 of this run: best-of-10 ("burst") and back-to-back ("sustained", power-capped clocks)
-                    k["executed_frac_of_tf32_peak"] = ach * mult / tf32["tf32_tflops"] if mult > 1 else None
-                    k["executed_frac_of_tf32_sustained"] = ach * mult / tf32["tf32_tflops_sustained"] if mult > 1 else None
+                    if mma_kind == "f16":
+                        # two-term fp16 operands: the MMAs run at the bf16 / fp16 rate, the contract's own yardstick
+                        k["executed_frac_of_bf16_sustained"] = ach * mult / pk["bf16_tflops_sustained"]
+                        k["executed_frac_of_tf32_peak"] = k["executed_frac_of_tf32_sustained"] = None
+                    else:
+                        # cuBLAS dense TF32 of this run: best-of-10 ("burst") and back-to-back ("sustained", power-capped clocks)
+                        k["executed_frac_of_tf32_peak"] = ach * mult / tf32["tf32_tflops"] if mult > 1 else None
+                        k["executed_frac_of_tf32_sustained"] = ach * mult / tf32["tf32_tflops_sustained"] if mult > 1 else None
                 kernels.append(k)
             breakdown["kernels"] = kernels
             if kernels:
@@ -674,8 +694,9 @@ def run_b200(a):
                                     "sustained for tensor kernels, copy bandwidth for the others); achieved = algorithmic "
                                     "work of the clouds AS EVALUATED (collapsed coalition clouds, see "
                                     "evaluated_clouds_by_points) / CUDA-event duration, averaged over the step's launches; "
-                                    "tensor kernels evaluate exact-fp32-grade products as 3 (Gram: 6) tf32 MMAs per MAC, "
-                                    "see executed_tflops; every kernel of the step is listed under `kernels`")
+                                    "tensor kernels evaluate exact-fp32-grade products as 3 (Gram: 6) MMAs per MAC -- tf32 "
+                                    "pairs, or two-term fp16 splits on kind::f16 (mma_kind) -- see executed_tflops; every "
+                                    "kernel of the step is listed under `kernels`")
 
     cpu = None
     if rig.rank == 0 and rig.world == 1 and not a.no_cpu_baseline:

@@ -38,6 +38,12 @@ uint64_t iq_launch_count(void);
  * are read once per process; this makes the next launch read them again (scripts/*_probe.py flip them in-process). */
 int iq_debug_reload_env(void);
 
+/* Which DGCNN / GCNN products currently run on kind::f16 tensor-core MMAs over two-term fp16 operand splits instead of
+ * 3xTF32 (same 22-bit operand accuracy, twice the MMA rate, half the operand bytes): bit 0 conv5 + pooling, bit 1 the
+ * tcgen05 EdgeConv products, bit 2 the Gram kNN nomination.  Library defaults, overridden by IQ_F16_CONV5 /
+ * IQ_F16_STORE / IQ_F16_GRAM = 0 | 1 (bench.py labels its roofline lines with it). */
+int iq_f16_paths(void);
+
 /* Per-kernel timing for bench.py's roofline leg: while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  iq_profile_report synchronises the device and returns the
  * number of distinct kernel names, filling up to `cap` (name, total milliseconds, launches) triples. */
@@ -193,7 +199,8 @@ int iq_topk_rows(const float *keys_dev, int64_t rows, int64_t N, int64_t ld, int
                  void *stream);
 
 /* y = act(x W^T + b): x (M,K), W (N,K), b (N) or NULL, act 0 none / 1 relu / 2 leaky_relu(0.2).
- * engine 0 = exact fp32 SIMT GEMM, 1 = tcgen05 3xTF32 GEMM (when built in). */
+ * engine 0 = exact fp32 SIMT GEMM, 1 = tcgen05 3xTF32 GEMM, 2 = tcgen05 kind::f16 on two-term fp16 splits of the
+ * operands (K % 8 == 0; iq_linear: N % 128 == 0, iq_linear_pool: points % 128 == 0) -- the form conv5 runs in. */
 int iq_linear(const float *x_dev, const float *w_dev, const float *b_dev, int64_t M, int64_t N, int64_t K, int act,
               int engine, float *y_dev, void *stream);
 

@@ -18,6 +18,7 @@ SIGNATURES = {
     "iq_last_error": (ctypes.c_char_p, []),
     "iq_launch_count": (ctypes.c_uint64, []),
     "iq_debug_reload_env": (_int, []),
+    "iq_f16_paths": (_int, []),
     "iq_profile_enable": (_int, [_int]),
     "iq_profile_report": (_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_longlong), _int]),
@@ -91,6 +92,11 @@ def last_error():
 
 def launch_count():
     return int(load().iq_launch_count())
+
+
+def f16_paths():
+    """Bit mask of the DGCNN / GCNN products running on kind::f16 MMAs: 1 conv5, 2 EdgeConv products, 4 Gram kNN."""
+    return int(load().iq_f16_paths())
 
 
 def profile_enable(on=True):

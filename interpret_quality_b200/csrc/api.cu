@@ -22,6 +22,8 @@ int iq_debug_reload_env(void)
     return 0;
 }
 
+int iq_f16_paths(void) { return f16_paths(); }
+
 int iq_profile_enable(int on)
 {
     profile_enable(on != 0);
@@ -220,9 +222,17 @@ int iq_knn_features(const float *x, int64_t B, int64_t N, int64_t C, int k, int3
     float *hi = reinterpret_cast<float *>(buf), *lo = hi + nf, *nxx = lo + nf;
     int32_t *cnt = reinterpret_cast<int32_t *>(nxx + rows);
     uint32_t *cand = reinterpret_cast<uint32_t *>(cnt + rows);
-    int rc = launch_split_tf32(x, rows, (int)C, C, hi, lo, C, st);
+    int rc = 0;
+    KnnOperands16 h16;
+    const bool f16 = (f16_paths() & F16_GRAM) != 0;      // the operand format the DGCNN forward nominates with
+    if (f16) {                                            // the fp16 pair of 8 x reuses the tf32 scratch
+        h16.hi = reinterpret_cast<__half *>(hi); h16.lo = reinterpret_cast<__half *>(lo); h16.ld = C; h16.scale = 8.0f;
+        rc = launch_split_f16(x, rows, (int)C, C, 8.0f, reinterpret_cast<__half *>(hi), reinterpret_cast<__half *>(lo), C, st);
+    } else {
+        rc = launch_split_tf32(x, rows, (int)C, C, hi, lo, C, st);
+    }
     if (!rc) rc = launch_sqnorm_rows(x, rows, (int)C, C, nxx, st);
-    if (!rc) rc = launch_knn_features_tc(x, hi, lo, C, (int)C, nxx, 1, B, N, k, cand, cnt, idx, st);
+    if (!rc) rc = launch_knn_features_tc(x, hi, lo, C, (int)C, nxx, 1, B, N, k, cand, cnt, idx, st, f16 ? &h16 : nullptr);
     if (!rc && cand_count && cudaMemcpyAsync(cand_count, cnt, sizeof(int32_t) * rows, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         rc = -2;
     cudaStreamSynchronize(st);
@@ -272,6 +282,23 @@ int iq_linear(const float *x, const float *w, const float *b, int64_t M, int64_t
         cudaFree(buf);
         return rc;
     }
+    if (engine == 2) {
+        // unit-test path of the kind::f16 form: two-term fp16 splits of x * 8 and w * 256 (powers of two: exact)
+        IQ_CHECK(K % 8 == 0, "iq_linear: the fp16 engine needs K % 8 == 0");
+        __half *buf = nullptr;
+        const size_t na = (size_t)M * K, nb = (size_t)N * K;
+        IQ_CUDA(cudaMalloc(&buf, sizeof(__half) * 2 * (na + nb)));
+        cudaStream_t st = as_stream(stream);
+        int rc = launch_split_f16(x, M, (int)K, K, 8.0f, buf, buf + na, K, st);
+        if (!rc) rc = launch_split_f16(w, N, (int)K, K, 256.0f, buf + 2 * na, buf + 2 * na + nb, K, st);
+        TcGemm t;
+        t.Ah_hi = buf; t.Ah_lo = buf + na; t.lda = K; t.Bh_hi = buf + 2 * na; t.Bh_lo = buf + 2 * na + nb; t.ldb = K;
+        t.K = (int)K; t.M = (int)M; t.N = (int)N; t.C = y; t.ldc = N; t.bias = b; t.act = act; t.alpha = 1.0f / 2048.0f;
+        if (!rc) rc = launch_gemm_tc(t, st);
+        cudaStreamSynchronize(st);
+        cudaFree(buf);
+        return rc;
+    }
     IQ_CHECK(engine == 0, "iq_linear: unknown engine");
     GemmDesc g;
     g.A = x; g.lda = K; g.B = w; g.ldb = K; g.C = y; g.ldc = N;
@@ -296,6 +323,24 @@ int iq_linear_pool(const float *x, const float *w, const float *b, int64_t cloud
         t.A_hi = buf + 2 * na; t.A_lo = buf + 2 * na + nb; t.lda = K; t.B_hi = buf; t.B_lo = buf + na; t.ldb = K;
         t.K = (int)K; t.clouds = (int)clouds; t.points = (int)points; t.cout = (int)N;
         t.out_max = out_max; t.out_mean = out_mean; t.out_arg = out_arg; t.ld_out = N; t.bias = b; t.act = act;
+        if (!rc) rc = launch_gemm_tc(t, st);
+        cudaStreamSynchronize(st);
+        cudaFree(buf);
+        return rc;
+    }
+    if (engine == 2) {
+        IQ_CHECK(K % 8 == 0, "iq_linear_pool: the fp16 engine needs K % 8 == 0");
+        __half *buf = nullptr;
+        const size_t na = (size_t)M * K, nb = (size_t)N * K;
+        IQ_CUDA(cudaMalloc(&buf, sizeof(__half) * 2 * (na + nb)));
+        int rc = launch_split_f16(x, M, (int)K, K, 8.0f, buf, buf + na, K, st);
+        if (!rc) rc = launch_split_f16(w, N, (int)K, K, 256.0f, buf + 2 * na, buf + 2 * na + nb, K, st);
+        TcGemm t;
+        t.mode = 1;
+        t.Ah_hi = buf + 2 * na; t.Ah_lo = buf + 2 * na + nb; t.lda = K; t.Bh_hi = buf; t.Bh_lo = buf + na; t.ldb = K;
+        t.K = (int)K; t.clouds = (int)clouds; t.points = (int)points; t.cout = (int)N;
+        t.out_max = out_max; t.out_mean = out_mean; t.out_arg = out_arg; t.ld_out = N; t.bias = b; t.act = act;
+        t.alpha = 1.0f / 2048.0f;
         if (!rc) rc = launch_gemm_tc(t, st);
         cudaStreamSynchronize(st);
         cudaFree(buf);

@@ -1,5 +1,6 @@
 // Shared helpers for the iq_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,6 +40,12 @@ int ensure_dynamic_smem(const void *func, int bytes);
 // environment switches of the diagnostics scripts, read once per process
 int env_int(const char *name, int fallback);
 void env_forget();                 // the next env_int() reads the environment again (iq_debug_reload_env)
+// Which DGCNN / GCNN products run on kind::f16 MMAs over two-term fp16 operands instead of 3xTF32 (edgeconv_model.cu):
+// bit 0 conv5 + pooling, bit 1 the tcgen05 EdgeConv products, bit 2 the Gram kNN nomination (bits 1-2 need bit 0, whose
+// fp16 activation buffers they read).  Defaults below, overridden by IQ_F16_CONV5 / IQ_F16_STORE / IQ_F16_GRAM = 0 | 1.
+enum : int { F16_CONV5 = 1, F16_STORE = 2, F16_GRAM = 4 };
+constexpr int F16_DEFAULT_PATHS = F16_CONV5 | F16_STORE | F16_GRAM;
+int f16_paths();
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -67,6 +74,21 @@ __device__ __forceinline__ float apply_act(float v, int act)
     if (act == ACT_RELU) return fmaxf(v, 0.0f);
     if (act == ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
     return v;
+}
+
+// Two-term fp16 split of x * scale for the kind::f16 tensor-core products (gemm_tc.cu): hi = fp16(xs), lo = fp16(xs - hi).
+// 22 significand bits (the tf32 pair has 21) while lo is a normal fp16 number, |xs| >= 2^-3; below that the absolute error
+// is <= 2^-25 (the fp16 subnormal spacing), i.e. 2^-25 / scale on x.  Conversions saturate at +-65504 instead of
+// producing infinities: hi + lo follows x up to |xs| = 131008 (with 2^-12 relative accuracy beyond 65504).
+__host__ __device__ __forceinline__ void split_f16(float x, float scale, __half &hi, __half &lo)
+{
+    const float xs = x * scale;
+    hi = __float2half_rn(fminf(fmaxf(xs, -65504.0f), 65504.0f));
+    lo = __float2half_rn(fminf(fmaxf(xs - __half2float(hi), -65504.0f), 65504.0f));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b)
+{
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
 // monotone float -> uint key (larger float <=> larger uint); -0.0 sorts just below +0.0

@@ -18,8 +18,14 @@ namespace iq {
 
 namespace {
 
+// Activations that feed kind::f16 products are stored as two-term fp16 splits of x * 8 (common.cuh, split_f16): full
+// 22-bit accuracy down to |x| = 2^-6, absolute error 4e-9 below, saturation only beyond |x| = 8188.
+constexpr float H_ACT_SCALE = 8.0f;
+
 struct EdgeLayer {
     float *wcat_hi = nullptr, *wcat_lo = nullptr;   // tf32 split of wcat
+    __half *wcat_h_hi = nullptr, *wcat_h_lo = nullptr;   // two-term fp16 split of wcat * h_scale
+    float h_scale = 1.0f;
     float *wcat = nullptr;       // (2*cout, cin): rows [0,cout) = s*Wa, rows [cout,2cout) = s*(Wb - Wa)
     float *bcat = nullptr;       // (2*cout): [0 ; t]
     int cin = 0, cout = 0, col = 0;
@@ -80,6 +86,15 @@ protected:
         float *pq = ws.take<float>(rows * 512);
         float *feat_hi = tc ? ws.take<float>(rows * 512) : nullptr;
         float *feat_lo = tc ? ws.take<float>(rows * 512) : nullptr;
+        // conv5 (and, as an experiment, the tcgen05 EdgeConv products) on kind::f16 MMAs: two-term fp16 operands carry the
+        // 22 significand bits of the tf32 pair at twice the MMA rate and half the bytes (gemm_tc.cu).  The buffers are
+        // taken whatever the switches say, so the workspace size does not depend on the environment.
+        __half *feat_h_hi = tc ? ws.take<__half>(rows * 512) : nullptr;
+        __half *feat_h_lo = tc ? ws.take<__half>(rows * 512) : nullptr;
+        const int h_paths = f16_paths();
+        const bool h_conv5 = tc && conv5.w_h_hi && (h_paths & F16_CONV5);
+        const bool h_store = h_conv5 && (h_paths & F16_STORE);
+        const bool h_gram = h_conv5 && tc_knn && (h_paths & F16_GRAM);   // the Gram kNN nominates on kind::f16 too
         float *dist = (dynamic && !tc_knn) ? ws.take<float>(Bc * N * N) : nullptr;
         const int tiles = (int)(N / 128);
         float *pmax = aligned ? ws.take<float>(Bc * tiles * 1024) : nullptr;
@@ -105,8 +120,10 @@ protected:
             // only nominate candidates; the k neighbours are decided on directly evaluated distances (knn_tc.cu).
             // Downstream-only products (last EdgeConv, conv5) and GCNN run on tcgen05 3xTF32.
             if (l > 0 && tc_knn) {
+                KnnOperands16 g16;
+                g16.hi = feat_h_hi + layers[l - 1].col; g16.lo = feat_h_lo + layers[l - 1].col; g16.ld = 512; g16.scale = H_ACT_SCALE;
                 if (int rc = launch_knn_features_tc(in, feat_hi + layers[l - 1].col, feat_lo + layers[l - 1].col, 512,
-                                                    L.cin, nxx, nxx_parts, Bc, N, k, cand, cnt, idx, st))
+                                                    L.cin, nxx, nxx_parts, Bc, N, k, cand, cnt, idx, st, h_gram ? &g16 : nullptr))
                     return rc;
             } else if (l > 0 && dynamic) {
                 GemmDesc d;
@@ -121,11 +138,16 @@ protected:
             const bool tc_all = env_int("IQ_TC_ALL", 0) != 0;            // experiment: EdgeConv 2-3 P|Q on tcgen05 too
             if (l > 0 && tc && (!dynamic || l == 3 || tc_all)) {
                 TcGemm p;
+                if (h_store && !(dynamic && l < 3)) {
+                    p.Ah_hi = feat_h_hi + layers[l - 1].col; p.Ah_lo = feat_h_lo + layers[l - 1].col;
+                    p.Bh_hi = L.wcat_h_hi; p.Bh_lo = L.wcat_h_lo;
+                    p.alpha = 1.0f / (H_ACT_SCALE * L.h_scale);
+                }
                 p.A_hi = feat_hi + layers[l - 1].col; p.A_lo = feat_lo + layers[l - 1].col; p.lda = 512;
                 p.B_hi = L.wcat_hi; p.B_lo = L.wcat_lo; p.ldb = L.cin;
                 p.K = L.cin; p.M = (int)rows; p.N = 2 * L.cout; p.C = pq; p.ldc = 2 * L.cout; p.bias = L.bcat;
                 p.tag = "tc_edge_pq";
-                p.four_terms = (dynamic && l < 3) ? 1 : 0;      // upstream of a dynamic kNN (IQ_TC_ALL experiment): 4xTF32
+                p.four_terms = (dynamic && l < 3) ? 1 : 0;      // upstream of a dynamic kNN (IQ_TC_ALL experiment): 4xTF32 (never fp16)
                 if (int rc = launch_gemm_tc(p, st)) return rc;
             } else {
                 GemmDesc p;
@@ -133,10 +155,16 @@ protected:
                 p.M = (int)rows; p.N = 2 * L.cout; p.K = L.cin; p.bias = L.bcat; p.tag = "sgemm_edge_pq";
                 if (int rc = launch_sgemm(p, st)) return rc;
             }
-            if (int rc = launch_gather_max(pq, 2 * L.cout, idx, Bc, N, k, L.cout, ACT_LRELU, feat + L.col, 512,
+            // who reads this layer's output: fp32 -- the SIMT products, the exact re-rank and the fp32 conv5; the tf32 pair --
+            // the Gram kNN and the tf32 tcgen05 products; the fp16 pair -- the kind::f16 products
+            const bool need_f32 = !tc || (dynamic && l < 3);
+            const bool need_tf32 = tc && (!h_conv5 || (l < 3 && ((tc_knn && !h_gram) || tc_all || !h_store)));
+            GatherOut16 h16;
+            if (h_conv5) { h16.hi = feat_h_hi + L.col; h16.lo = feat_h_lo + L.col; h16.ld = 512; h16.scale = H_ACT_SCALE; }
+            if (int rc = launch_gather_max(pq, 2 * L.cout, idx, Bc, N, k, L.cout, ACT_LRELU, need_f32 ? feat + L.col : nullptr, 512,
                                            (dynamic && l < 3) ? nxx : nullptr, tc_knn ? &nxx_parts : nullptr,
-                                           tc ? feat_hi + L.col : nullptr,
-                                           tc ? feat_lo + L.col : nullptr, st))
+                                           need_tf32 ? feat_hi + L.col : nullptr,
+                                           need_tf32 ? feat_lo + L.col : nullptr, h_conv5 ? &h16 : nullptr, st))
                 return rc;
         }
         if (tc) {
@@ -144,6 +172,10 @@ protected:
             c5.mode = 1;
             c5.A_hi = conv5.w_hi; c5.A_lo = conv5.w_lo; c5.lda = 512;
             c5.B_hi = feat_hi; c5.B_lo = feat_lo; c5.ldb = 512; c5.K = 512;
+            if (h_conv5) {
+                c5.Ah_hi = conv5.w_h_hi; c5.Ah_lo = conv5.w_h_lo; c5.Bh_hi = feat_h_hi; c5.Bh_lo = feat_h_lo;
+                c5.alpha = 1.0f / (H_ACT_SCALE * conv5.h_scale);
+            }
             c5.clouds = (int)Bc; c5.points = (int)N; c5.cout = 1024;
             c5.out_max = g; c5.out_mean = g + 1024; c5.ld_out = 2048; c5.bias = conv5.b; c5.act = ACT_LRELU;
             c5.pool_extra = cur_.pool_extra;
@@ -193,8 +225,12 @@ Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int
         L.cin = cin[l]; L.cout = cout[l]; L.col = col[l];
         std::vector<float> whi, wlo;
         split_tf32_host(wcat, whi, wlo);
+        std::vector<__half> hhi, hlo;
+        L.h_scale = split_f16_host(wcat, hhi, hlo);
         if (m->arena_.upload(wcat, &L.wcat) || m->arena_.upload(bcat, &L.bcat) || m->arena_.upload(whi, &L.wcat_hi) ||
-            m->arena_.upload(wlo, &L.wcat_lo)) {
+            m->arena_.upload(wlo, &L.wcat_lo) ||
+            m->arena_.upload_bytes(hhi.data(), hhi.size() * sizeof(__half), reinterpret_cast<void **>(&L.wcat_h_hi)) ||
+            m->arena_.upload_bytes(hlo.data(), hlo.size() * sizeof(__half), reinterpret_cast<void **>(&L.wcat_h_lo))) {
             err = last_error();
             return nullptr;
         }
@@ -214,6 +250,15 @@ Model *create_edgeconv_model(const StateDict &sd, bool dynamic_graph, int k, int
             m->arena_.upload(wlo, &e.d->w_lo)) {
             err = last_error();
             return nullptr;
+        }
+        if (e.d == &m->conv5) {
+            std::vector<__half> hhi, hlo;
+            e.d->h_scale = split_f16_host(w, hhi, hlo);
+            if (m->arena_.upload_bytes(hhi.data(), hhi.size() * sizeof(__half), reinterpret_cast<void **>(&e.d->w_h_hi)) ||
+                m->arena_.upload_bytes(hlo.data(), hlo.size() * sizeof(__half), reinterpret_cast<void **>(&e.d->w_h_lo))) {
+                err = last_error();
+                return nullptr;
+            }
         }
     }
     return m.release();

@@ -2,6 +2,10 @@
 //
 //   D[m][n] = sum_k A[m][k] * B[n][k]          A (M,K), B (N,K) both K-major fp32
 //
+// Operand formats: tf32 hi/lo pairs (kind::tf32, 32 elements per 128-byte swizzle row) or, template flag H, two-term
+// fp16 splits of the scaled operands (kind::f16, 64 elements per row: same bytes per stage, same descriptors, same
+// three products, twice the K per MMA at the same MMA time -- half the stages and half the operand bytes per product).
+//
 // Single-pass TF32 (and BF16) fails the 1e-3 parity bar for every model of the
 // reference, DGCNN worst because a rounded kNN key flips neighbours
 // (SURVEY.md section 7.2), so each fp32 operand is pre-split by its producer into
@@ -127,7 +131,7 @@ __device__ __forceinline__ void store_box(const CUtensorMap *map, const float (&
 // unswitching / unrolling choices for one variant moved whenever another was touched (POOL 85 -> 130 ms on PointNet++
 // after an unrelated edit).
 enum : int { VAR_STORE = 0, VAR_POOL_RUN = 1, VAR_POOL_TILE = 2, VAR_STORE_GATHER = 3, VAR_POOL_RUN_ATM = 4, VAR_POOL_TILE_ATM = 5 };
-template <int BN, int STAGES, int VAR>
+template <int BN, int STAGES, int VAR, bool H = false>
 __global__ void __launch_bounds__(TC_THREADS + (VAR == VAR_STORE_GATHER ? GA_THREADS : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
@@ -143,6 +147,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     constexpr bool STORE = VAR == VAR_STORE || VAR == VAR_STORE_GATHER;
     constexpr bool POOL_RUN = VAR == VAR_POOL_RUN || VAR == VAR_POOL_RUN_ATM;   // groups of >= BN columns: running reduction
     static_assert(!ATM || BN == 128, "the TMEM-resident A variants use 128-column tiles");
+    static_assert(!H || (!ATM && !GA), "fp16 operands: plain STORE / POOL only");
+    constexpr int KE = H ? 2 * TBK : TBK;                                  // K elements per 128-byte row = per ring stage
     constexpr uint32_t TMEM_COLS = ATM ? 512u : (uint32_t)tmem_cols_for(BN);
     constexpr uint32_t A_COL = 256;                                         // ATM: A hi at columns [256, 384), lo at [384, 512)
     constexpr uint32_t FULL_ARRIVALS = GA ? 5 : 1;                          // TMA producer (+ the four gather warps)
@@ -157,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = (p.K + TBK - 1) / TBK;          // TMA zero-fills the K tail
+    const int kblocks = (p.K + KE - 1) / KE;            // TMA zero-fills the K tail
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_ahi); prefetch_tmap(&map_alo); prefetch_tmap(&map_bhi); prefetch_tmap(&map_blo);
@@ -202,18 +208,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&full_bar[stage], GA ? 2 * S::B_BYTES : S::STAGE_BYTES);
                         if (!GA && !ATM) {
-                            tma_load_2d(st, &map_ahi, &full_bar[stage], kb * TBK, a_row0);
-                            tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * TBK, a_row0);
+                            tma_load_2d(st, &map_ahi, &full_bar[stage], kb * KE, a_row0);
+                            tma_load_2d(st + S::A_BYTES, &map_alo, &full_bar[stage], kb * KE, a_row0);
                         }
-                        tma_load_2d(st + 2 * S::A_BYTES, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
-                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_blo, &full_bar[stage], kb * TBK, b_row0);
+                        tma_load_2d(st + 2 * S::A_BYTES, &map_bhi, &full_bar[stage], kb * KE, b_row0);
+                        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &map_blo, &full_bar[stage], kb * KE, b_row0);
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(BN);
+        constexpr uint32_t idesc = H ? make_idesc_f16(BN) : make_idesc(BN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         if (ATM) {                                                          // the epilogue warps have parked this CTA's A tile
@@ -233,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     const uint64_t bhi = make_smem_desc(sbase + 2 * S::A_BYTES);
                     const uint64_t blo = make_smem_desc(sbase + 2 * S::A_BYTES + S::B_BYTES);
                     if (elect_one_sync()) {
-                        if (!ATM && p.four_terms) {
+                        if (!ATM && !H && p.four_terms) {
 #pragma unroll
                             for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
                                 const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
@@ -250,6 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                                 if (ATM)
                                     umma_tf32_ts(d_tmem, tmem_base + A_COL + (term == 0 ? 128u : 0u) + (uint32_t)(kb * TBK + ks * UMMA_K),
                                                  bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
+                                else if (H)                              // one k-step = the same 32 bytes = 16 fp16
+                                    umma_f16(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks) != 0 ? 1u : 0u);
                                 else
                                     umma_tf32(d_tmem, ad + koff, bd + koff, idesc, (kb | term | ks | p.four_terms) != 0 ? 1u : 0u);
                             }
@@ -474,6 +482,37 @@ int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float
     return 0;
 }
 
+namespace {
+__global__ void split_f16_kernel(const float *__restrict__ x, int64_t rows, int cols, int64_t ldx, float scale,
+                                 __half *__restrict__ hi, __half *__restrict__ lo, int64_t ldo)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cv = cols >> 2;
+    if (t >= rows * cv) return;
+    const int64_t r = t / cv;
+    const int c = (int)(t - r * cv) << 2;
+    const float4 v = *reinterpret_cast<const float4 *>(x + r * ldx + c);
+    __half h0, h1, h2, h3, l0, l1, l2, l3;
+    split_f16(v.x, scale, h0, l0); split_f16(v.y, scale, h1, l1);
+    split_f16(v.z, scale, h2, l2); split_f16(v.w, scale, h3, l3);
+    *reinterpret_cast<uint2 *>(hi + r * ldo + c) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+    *reinterpret_cast<uint2 *>(lo + r * ldo + c) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+}
+}  // namespace
+
+int launch_split_f16(const float *x, int64_t rows, int cols, int64_t ldx, float scale, __half *hi, __half *lo, int64_t ldo,
+                     cudaStream_t st)
+{
+    ProfileScope _ps("split_f16", st);
+    IQ_CHECK(cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "split_f16: widths must be multiples of 4");
+    if (rows == 0) return 0;
+    const int64_t n = rows * (cols / 4);
+    split_f16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, rows, cols, ldx, scale, hi, lo, ldo);
+    IQ_COUNT_LAUNCH();
+    IQ_LAUNCH_CHECK();
+    return 0;
+}
+
 static int pick_bn(int n)
 {
     for (int bn : {128, 96, 64, 32})
@@ -492,20 +531,27 @@ bool tc_gemm_supported(const TcGemm &g)
     return 128 % g.points == 0 && ((int64_t)g.clouds * g.points) % 128 == 0;
 }
 
-template <int BN, int STAGES, int VAR>
+template <int BN, int STAGES, int VAR, bool H = false>
 static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_t b_rows, cudaStream_t st)
 {
     constexpr bool ATM = VAR == VAR_POOL_RUN_ATM || VAR == VAR_POOL_TILE_ATM;
     using S = TcSmem<BN, STAGES, ATM>;
     CUtensorMap mahi, malo, mbhi, mblo;
-    if (int rc = make_map(&mbhi, g.B_hi, b_rows, g.K, g.ldb, BN)) return rc;
-    if (int rc = make_map(&mblo, g.B_lo, b_rows, g.K, g.ldb, BN)) return rc;
     constexpr bool GA = VAR == VAR_STORE_GATHER;
-    if (GA) {
-        mahi = mbhi; malo = mblo;                               // unused: the A tiles are produced in the kernel
+    if (H) {
+        if (int rc = make_map_any(&mbhi, g.Bh_hi, b_rows, g.K, g.ldb, BN, 2)) return rc;
+        if (int rc = make_map_any(&mblo, g.Bh_lo, b_rows, g.K, g.ldb, BN, 2)) return rc;
+        if (int rc = make_map_any(&mahi, g.Ah_hi, a_rows, g.K, g.lda, TBM, 2)) return rc;
+        if (int rc = make_map_any(&malo, g.Ah_lo, a_rows, g.K, g.lda, TBM, 2)) return rc;
     } else {
-        if (int rc = make_map(&mahi, g.A_hi, a_rows, g.K, g.lda, TBM)) return rc;
-        if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
+        if (int rc = make_map(&mbhi, g.B_hi, b_rows, g.K, g.ldb, BN)) return rc;
+        if (int rc = make_map(&mblo, g.B_lo, b_rows, g.K, g.ldb, BN)) return rc;
+        if (GA) {
+            mahi = mbhi; malo = mblo;                           // unused: the A tiles are produced in the kernel
+        } else {
+            if (int rc = make_map(&mahi, g.A_hi, a_rows, g.K, g.lda, TBM)) return rc;
+            if (int rc = make_map(&malo, g.A_lo, a_rows, g.K, g.lda, TBM)) return rc;
+        }
     }
     // STORE outputs leave through TMA: 32 x 32 boxes (128 bytes wide) over each fp32 output matrix
     CUtensorMap mc = mahi, mchi = mahi, mclo = mahi;
@@ -516,13 +562,13 @@ static int launch_tc_variant(const TcGemm &g, TcParams p, int64_t a_rows, int64_
             if (int rc = make_map(&mclo, g.C_lo, g.M, g.N, g.ldc, 32)) return rc;
         }
     }
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gemm_tc_kernel<BN, STAGES, VAR>), S::TOTAL)) return rc;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gemm_tc_kernel<BN, STAGES, VAR, H>), S::TOTAL)) return rc;
     int grid = std::min(p.num_units, sm_count());
     if (ATM) {                                                  // a CTA keeps one row tile of A: grid = multiple of m_tiles
         grid = std::max(p.m_tiles, grid / p.m_tiles * p.m_tiles);
         p.a_hi = g.A_hi; p.a_lo = g.A_lo; p.lda = g.lda; p.a_rows = (int)a_rows;
     }
-    gemm_tc_kernel<BN, STAGES, VAR><<<grid, TC_THREADS + (GA ? GA_THREADS : 0), S::TOTAL, st>>>(mahi, malo, mbhi, mblo, mc, mchi, mclo, p);
+    gemm_tc_kernel<BN, STAGES, VAR, H><<<grid, TC_THREADS + (GA ? GA_THREADS : 0), S::TOTAL, st>>>(mahi, malo, mbhi, mblo, mc, mchi, mclo, p);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -558,6 +604,17 @@ int launch_gemm_tc(const TcGemm &g, cudaStream_t st)
         IQ_CHECK(g.points >= bn || (!g.out_mean && !g.out_arg), "gemm_tc: mean / argmax need groups of >= 128 columns");
     }
     if (p.num_units == 0) return 0;
+    if (g.Ah_hi) {                                              // two-term fp16 operands (kind::f16)
+        IQ_CHECK(g.Ah_lo && g.Bh_hi && g.Bh_lo && !g.gather.U && g.rows_per_batch == 0 && !g.four_terms,
+                 "gemm_tc: fp16 operands take the plain STORE / POOL forms");
+        IQ_CHECK(g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm_tc: fp16 operands need K and leading dimensions in multiples of 8");
+        if (g.mode == 1) {
+            IQ_CHECK(g.points >= bn, "gemm_tc: fp16 POOL needs groups of >= 128 columns");
+            return launch_tc_variant<128, 3, VAR_POOL_RUN, true>(g, p, a_rows, b_rows, st);
+        }
+        IQ_CHECK(bn == 128, "gemm_tc: fp16 STORE needs N % 128 == 0");
+        return launch_tc_variant<128, 3, VAR_STORE, true>(g, p, a_rows, b_rows, st);
+    }
     if (g.gather.U) {
         IQ_CHECK(g.mode == 0 && g.N == bn, "gemm_tc: the gathered-A variant takes one column tile (N in {32, 64, 96, 128})");
         IQ_CHECK(g.gather.ldu % 4 == 0 && g.gather.ldv % 4 == 0 && g.K % 4 == 0, "gemm_tc: gathered-A widths must be multiples of 4");

@@ -333,7 +333,8 @@ template <int CPL>
 __global__ void __launch_bounds__(256)
 gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int64_t total, int N,
                   int k, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ neg_sqnorm,
-                  float *__restrict__ out_hi, float *__restrict__ out_lo)
+                  float *__restrict__ out_hi, float *__restrict__ out_lo, __half *__restrict__ h_hi,
+                  __half *__restrict__ h_lo, int64_t ldh, float hscale)
 {
     constexpr int Cout = CPL * 32;
     const int lane = threadIdx.x & 31;
@@ -371,13 +372,30 @@ gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__r
         res[c] = apply_act(mx[c] + qr[c], act);
         ss = fmaf(res[c], res[c], ss);
     }
-    float *o = out + i * ldo + lane * CPL;
-    if (CPL == 2) {
-        *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
-    } else {
+    if (out) {
+        float *o = out + i * ldo + lane * CPL;
+        if (CPL == 2) {
+            *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < CPL / 4; ++q)
-            *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+            for (int q = 0; q < CPL / 4; ++q)
+                *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+        }
+    }
+    if (h_hi) {                                                     // two-term fp16 split for the kind::f16 consumers
+        uint32_t wh[CPL / 2], wl[CPL / 2];
+#pragma unroll
+        for (int c = 0; c < CPL; c += 2) {
+            __half a, b, la, lb;
+            split_f16(res[c], hscale, a, la);
+            split_f16(res[c + 1], hscale, b, lb);
+            wh[c / 2] = pack_h2(a, b);
+            wl[c / 2] = pack_h2(la, lb);
+        }
+        uint32_t *dh = reinterpret_cast<uint32_t *>(h_hi + i * ldh + lane * CPL);
+        uint32_t *dl = reinterpret_cast<uint32_t *>(h_lo + i * ldh + lane * CPL);
+#pragma unroll
+        for (int c = 0; c < CPL / 2; ++c) { dh[c] = wh[c]; dl[c] = wl[c]; }
     }
     if (out_hi) {                                                   // tf32 hi/lo split for the tensor-core consumers
 #pragma unroll
@@ -404,7 +422,8 @@ constexpr int GMS_THREADS = 1024;             // one CTA per SM (the table fills
 __global__ void __launch_bounds__(GMS_THREADS)
 gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int N, int k, int Cout,
                        int psplit, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ out_hi,
-                       float *__restrict__ out_lo, float *__restrict__ sq_part)
+                       float *__restrict__ out_lo, float *__restrict__ sq_part, __half *__restrict__ h_hi,
+                       __half *__restrict__ h_lo, int64_t ldh, float hscale)
 {
     extern __shared__ float4 ptab[];                               // N rows x 8 float4
     const int slices = Cout >> 5;
@@ -412,16 +431,6 @@ gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t
     const int ps = unit % psplit, sl = (unit / psplit) % slices, cloud = unit / (psplit * slices);
     const int64_t cloud0 = (int64_t)cloud * N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ptab);
-        for (int t = tid; t < N * 8; t += GMS_THREADS) {
-            const int j = t >> 3, q = t & 7;
-            const float *src = PQ + (cloud0 + j) * ldpq + sl * 32 + q * 4;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)t * 16u), "l"(src) : "memory");
-        }
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
     const int g = lane >> 3, q = lane & 7;                          // 4 points per warp instruction, 8 lanes each
     const int per = N / psplit;
     const int p_end = (ps + 1) * per;
@@ -433,7 +442,17 @@ gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t
         return q < 5 ? __ldg(reinterpret_cast<const int4 *>(row) + q) : make_int4(0, 0, 0, 0);
     };
     int4 nb_next = make_int4(0, 0, 0, 0);
-    if (k == 20 && ps * per + warp * 4 < p_end) nb_next = load_nb(ps * per + warp * 4);
+    if (k == 20 && ps * per + warp * 4 < p_end) nb_next = load_nb(ps * per + warp * 4);   // in flight during the table fill
+    {
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ptab);
+        for (int t = tid; t < N * 8; t += GMS_THREADS) {
+            const int j = t >> 3, q = t & 7;
+            const float *src = PQ + (cloud0 + j) * ldpq + sl * 32 + q * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)t * 16u), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
     for (int p0 = ps * per + warp * 4; p0 < p_end; p0 += GMS_THREADS / 8) {
         const int i = p0 + g;
         const int32_t *row = idx + (cloud0 + i) * k;
@@ -464,7 +483,15 @@ gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t
         r.x = apply_act(mx.x + qv.x, act); r.y = apply_act(mx.y + qv.y, act);
         r.z = apply_act(mx.z + qv.z, act); r.w = apply_act(mx.w + qv.w, act);
         const int64_t o = (cloud0 + i) * ldo + sl * 32 + q * 4;
-        *reinterpret_cast<float4 *>(out + o) = r;
+        if (out) *reinterpret_cast<float4 *>(out + o) = r;
+        if (h_hi) {                                                 // two-term fp16 split for the kind::f16 consumers
+            __half h0, h1, h2, h3, l0, l1, l2, l3;
+            split_f16(r.x, hscale, h0, l0); split_f16(r.y, hscale, h1, l1);
+            split_f16(r.z, hscale, h2, l2); split_f16(r.w, hscale, h3, l3);
+            const int64_t oh = (cloud0 + i) * ldh + sl * 32 + q * 4;
+            *reinterpret_cast<uint2 *>(h_hi + oh) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+            *reinterpret_cast<uint2 *>(h_lo + oh) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+        }
         if (out_hi) {
             float4 h, l;
             h.x = __uint_as_float((__float_as_uint(r.x) + 0x1000u) & 0xffffe000u);
@@ -590,9 +617,16 @@ int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *o
 
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
                       int act, float *out, int64_t ldo, float *neg_sqnorm, int *sq_parts, float *out_hi, float *out_lo,
-                      cudaStream_t st)
+                      const GatherOut16 *h16, cudaStream_t st)
 {
     if (sq_parts) *sq_parts = 1;
+    __half *h_hi = h16 ? h16->hi : nullptr, *h_lo = h16 ? h16->lo : nullptr;
+    const int64_t ldh = h16 ? h16->ld : 0;
+    const float hscale = h16 ? h16->scale : 1.0f;
+    IQ_CHECK(out || h_hi || out_hi, "gather_max: no output");
+    IQ_CHECK(!out_hi || out_lo, "gather_max: the tf32 pair needs both halves");
+    IQ_CHECK(!h_hi || (h_lo && ldh % 8 == 0), "gather_max: fp16 outputs need both halves and a leading dimension that is a multiple of 8");
+    IQ_CHECK(out || !neg_sqnorm || sq_parts, "gather_max: the separate squared-norm pass reads the fp32 output");
     const int64_t total = B * N;
     if (total == 0) return 0;
     IQ_CHECK(Cout == 64 || Cout == 128 || Cout == 256, "gather_max: Cout must be 64, 128 or 256");
@@ -608,7 +642,7 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
             // the caller can take per-slice partial squared norms (sq_parts != null: |x_i|^2 = sum of Cout/32 parts)
             float *parts = (neg_sqnorm && sq_parts) ? neg_sqnorm : nullptr;
             gather_max_smem_kernel<<<(unsigned)(base_units * psplit), GMS_THREADS, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
-                                                                                       act, out, ldo, out_hi, out_lo, parts);
+                                                                                       act, out, ldo, out_hi, out_lo, parts, h_hi, h_lo, ldh, hscale);
             IQ_COUNT_LAUNCH();
             IQ_LAUNCH_CHECK();
             if (parts) *sq_parts = Cout / 32;
@@ -618,9 +652,9 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
     }
     ProfileScope _ps("gather_max", st);
     const unsigned grid = (unsigned)ceil_div(total * 32, 256);
-    if (Cout == 64) gather_max_kernel<2><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
-    else if (Cout == 128) gather_max_kernel<4><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
-    else gather_max_kernel<8><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo);
+    if (Cout == 64) gather_max_kernel<2><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo, h_hi, h_lo, ldh, hscale);
+    else if (Cout == 128) gather_max_kernel<4><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo, h_hi, h_lo, ldh, hscale);
+    else gather_max_kernel<8><<<grid, 256, 0, st>>>(PQ, ldpq, idx, total, (int)N, k, act, out, ldo, neg_sqnorm, out_hi, out_lo, h_hi, h_lo, ldh, hscale);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;

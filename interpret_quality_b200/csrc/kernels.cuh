@@ -65,6 +65,11 @@ int launch_pool_finish(const float *pmax, const int32_t *parg, const float *psum
 struct TcGemm {
     const float *A_hi = nullptr, *A_lo = nullptr;   // (rows, K) K-major, leading dimension lda
     const float *B_hi = nullptr, *B_lo = nullptr;   // (rows, K) K-major, leading dimension ldb
+    // Alternative operand format (when Ah_hi is set the four pointers above are ignored): two-term fp16 splits
+    // (common.cuh, split_f16) of A * sa and B * sb, same leading dimensions counted in halves (multiples of 8); the
+    // caller folds 1 / (sa * sb) into alpha.  kind::f16 MMAs run at twice the tf32 rate on half the operand bytes.
+    // Plain STORE (128-column tiles) and POOL with groups of >= 128 columns only.
+    const __half *Ah_hi = nullptr, *Ah_lo = nullptr, *Bh_hi = nullptr, *Bh_lo = nullptr;
     int64_t lda = 0, ldb = 0;
     int K = 0;
     int mode = 0;                 // 0 = STORE: C = act(alpha * A B^T + bias[col]);  1 = POOL (see gemm_tc.cu)
@@ -102,6 +107,8 @@ bool tc_gemm_supported(const TcGemm &g);
 int launch_gemm_tc(const TcGemm &g, cudaStream_t st);
 int launch_split_tf32(const float *x, int64_t rows, int cols, int64_t ldx, float *hi, float *lo, int64_t ldo,
                       cudaStream_t st);
+int launch_split_f16(const float *x, int64_t rows, int cols, int64_t ldx, float scale, __half *hi, __half *lo, int64_t ldo,
+                     cudaStream_t st);
 
 // chain_tc.cu -- one grouped shared MLP of a set-abstraction scale in one kernel:
 //   out[g] = max over the K rows of group g of relu(relu(relu(U[idx] - V + b1) W2^T + b2) W3^T + b3)
@@ -128,9 +135,16 @@ bool knn_features_tc_supported(int64_t N, int C, int k);
 // x (clouds*N, C) fp32 with leading dimension ld, x_hi / x_lo its tf32 split (same ld); nxx (rows, nxx_parts): the
 // squared norm of row j is |sum_p nxx[j][p]| (one negated value, or positive partial sums);
 // scratch: masks (rows, 2, N/32) u32, cnt (rows) i32; out idx (rows, k): the SET of the k nearest by (distance, index)
+// h16 (optional): nominate on kind::f16 MMAs over the two-term fp16 split of scale * x instead of the tf32 pair
+// (x_hi / x_lo are then not read); the exact re-rank reads the fp32 rows either way
+struct KnnOperands16 {
+    const __half *hi = nullptr, *lo = nullptr;
+    int64_t ld = 0;               // leading dimension in halves, multiple of 8
+    float scale = 1.0f;
+};
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
                            int nxx_parts, int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
-                           cudaStream_t st);
+                           cudaStream_t st, const KnnOperands16 *h16 = nullptr);
 
 // graph.cu
 int launch_knn_xyz(const float *xyz, int point_major, int64_t B, int64_t N, int k, int32_t *idx, cudaStream_t st);
@@ -143,9 +157,16 @@ int launch_knn_rerank(const float *x, int64_t ld, int C, const int32_t *cand, in
 int launch_sqnorm_rows(const float *x, int64_t rows, int C, int64_t ld, float *out, cudaStream_t st);
 // neg_sqnorm (optional): -|out_i|^2 per row; when sq_parts is given the kernel may instead leave *sq_parts positive
 // partial sums per row, (rows, *sq_parts), whose total is |out_i|^2 (buffer of rows * Cout/32 floats)
+// h16 (optional): also leave the rows as a two-term fp16 split of out * scale (split_f16) for a kind::f16 consumer;
+// `out` may then be null (no fp32 consumer)
+struct GatherOut16 {
+    __half *hi = nullptr, *lo = nullptr;
+    int64_t ld = 0;               // leading dimension in halves, multiple of 8
+    float scale = 1.0f;
+};
 int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t B, int64_t N, int k, int Cout,
                       int act, float *out, int64_t ldo, float *neg_sqnorm, int *sq_parts, float *out_hi, float *out_lo,
-                      cudaStream_t st);
+                      const GatherOut16 *h16, cudaStream_t st);
 int launch_xyz_to_point_major(const float *x_cf, int64_t B, int64_t N, float *x_pm, cudaStream_t st);
 
 // grouping.cu

@@ -51,8 +51,9 @@ struct KnnParams {
     int points;            // N, multiple of 128
     int m_tiles;           // N / 128
     int num_units;         // clouds * m_tiles
-    const float *x_hi, *x_lo;   // tf32 split of the features, leading dimension ld (the A rows are read directly)
-    int64_t ld;
+    const void *x_hi, *x_lo;    // tf32 (or two-term fp16, template flag H) split of the features; the A rows are read directly
+    int64_t ld_bytes;           // bytes between rows
+    float key_scale;            // key = key_scale * G - |x_j|^2: 2, or 2 / s^2 when the fp16 operands carry s * x
     const float *nxx;      // (rows, nxx_parts): |x_j|^2 = |sum of the parts|
     int nxx_parts;
     uint32_t *masks;       // (rows, 2, N/32): bit j of [row][0] <=> key > T0, of [row][1] <=> key == T0
@@ -94,7 +95,10 @@ __device__ __forceinline__ void sort_desc(float (&a)[W])
     }
 }
 
-template <int BN, int STAGES, int KMAX>
+// H: the operands are two-term fp16 splits (kind::f16 MMAs, 64 elements per 128-byte row): half the MMAs, half the
+// operand bytes, the same three products.  In TMEM the A tile then holds two fp16 per column, so every column offset below
+// (32 per ring stage, 8 per k-step) is the same in both formats; A takes KMAX / 2 columns per half instead of KMAX.
+template <int BN, int STAGES, int KMAX, bool H = false>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                 const KnnParams p)
@@ -105,8 +109,10 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
     constexpr int HG = HC / 32;                                      // 32-column TMEM loads per warp and tile
     static_assert(HC >= KNN_NOM, "each half must track at least NOM blocks");
     static_assert(KMAX == 64 || KMAX == 128, "feature width is 64 or 128");
-    constexpr int NACC = (512 - 2 * KMAX) / BN;                      // accumulator buffers: TMEM columns [0, NACC*BN)
-    constexpr uint32_t A_COL = NACC * BN;                            // A hi at [A_COL, A_COL+KMAX), lo right after
+    constexpr int KE = H ? 2 * TBK : TBK;                            // K elements per 128-byte row = per ring stage
+    constexpr int AW = H ? KMAX / 2 : KMAX;                          // TMEM columns of one half (hi or lo) of the A tile
+    constexpr int NACC = (512 - 2 * AW) / BN;                        // accumulator buffers: TMEM columns [0, NACC*BN)
+    constexpr uint32_t A_COL = NACC * BN;                            // A hi at [A_COL, A_COL+AW), lo right after
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *b_smem = smem;
@@ -122,7 +128,7 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = (p.K + TBK - 1) / TBK;
+    const int kblocks = (p.K + KE - 1) / KE;
     const int T = p.points / BN;                                     // column tiles per sweep
     constexpr uint32_t TMEM_COLS = 512;
 
@@ -157,8 +163,8 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
                             mbar_arrive(&full_bar[stage]);
                         } else {
                             mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                            tma_load_2d(st, &map_bhi, &full_bar[stage], kb * TBK, b_row0);
-                            tma_load_2d(st + S::B_TILE, &map_blo, &full_bar[stage], kb * TBK, b_row0);
+                            tma_load_2d(st, &map_bhi, &full_bar[stage], kb * KE, b_row0);
+                            tma_load_2d(st + S::B_TILE, &map_blo, &full_bar[stage], kb * KE, b_row0);
                         }
                     }
                     __syncwarp();
@@ -168,7 +174,7 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
         }
     } else if (warp == 1) {
         // the whole warp walks the schedule (uniform control flow); one elected lane issues the MMAs and commits
-        constexpr uint32_t idesc = make_idesc(BN);
+        constexpr uint32_t idesc = H ? make_idesc_f16(BN) : make_idesc(BN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
         long long c_a = 0, c_acc = 0, c_full = 0, c_issue = 0, c0 = 0, c1 = 0;   // IQ_KNN_DBG & 16: where the issuer waits
@@ -192,7 +198,7 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
                     if (prof) { c1 = clock64(); c_full += c1 - c0; }
                     tc_fence_after();
                     const uint32_t sbase = smem_u32(b_smem + stage * S::STAGE_BYTES);
-                    const uint32_t ahi = tmem_base + A_COL + (uint32_t)(kb * TBK), alo = ahi + KMAX;
+                    const uint32_t ahi = tmem_base + A_COL + (uint32_t)(kb * TBK), alo = ahi + AW;
                     const uint64_t bhi = make_smem_desc(sbase), blo = make_smem_desc(sbase + S::B_TILE);
                     if (elect_one_sync()) {
                         if (!(p.dbg & 2)) {
@@ -203,8 +209,12 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
 #pragma unroll
                                 for (int ks = 0; ks < TBK / UMMA_K; ++ks) {
                                     const uint64_t koff = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                                    umma_tf32_ts(d_tmem, ad + (uint32_t)(ks * UMMA_K), bd + koff, idesc,
-                                                 (kb | term | ks) != 0 ? 1u : 0u);
+                                    if (H)
+                                        umma_f16_ts(d_tmem, ad + (uint32_t)(ks * UMMA_K), bd + koff, idesc,
+                                                    (kb | term | ks) != 0 ? 1u : 0u);
+                                    else
+                                        umma_tf32_ts(d_tmem, ad + (uint32_t)(ks * UMMA_K), bd + koff, idesc,
+                                                     (kb | term | ks) != 0 ? 1u : 0u);
                                 }
                             }
                         }
@@ -230,6 +240,7 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
         const int etid = threadIdx.x - 64;                           // 0..255 among the epilogue threads
         const uint32_t nb_s = smem_u32(nb);
         const int words = p.points >> 5;
+        const float ksc = p.key_scale;
         int acc = 0;
         uint32_t acc_phase = 0, a_phase = 0;
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -241,29 +252,31 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
             // pipe idle), so each warp loads its 32 rows coalesced (4 rows x 128 B per instruction), transposes them
             // through a 128B-swizzled 4 KB tile of shared memory and only then takes one row per lane.
             {
-                const float *src = (half ? p.x_lo : p.x_hi) + (cloud_row0 + mt * TBM + quad * 32) * p.ld;
-                const uint32_t a_t = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL + (uint32_t)(half * KMAX);
+                // (byte arithmetic: a pass moves 128 bytes of each row = 32 TMEM columns in either operand format)
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(half ? p.x_lo : p.x_hi) +
+                                     (cloud_row0 + mt * TBM + quad * 32) * p.ld_bytes;
+                const uint32_t a_t = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL + (uint32_t)(half * AW);
                 const uint32_t stg = smem_u32(a_xpose) + (uint32_t)(warp - 2) * 4096u;
                 const int lr = lane >> 3, lq = lane & 7;
                 float4 g[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it)
-                    g[it] = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(it * 4 + lr) * p.ld) + lq);
+                    g[it] = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(it * 4 + lr) * p.ld_bytes) + lq);
                 mbar_wait(a_empty, a_phase ^ 1);                     // MMAs of the previous unit have retired
                 a_phase ^= 1;
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < KMAX / 32; ++c) {
+                for (int c = 0; c < AW / 32; ++c) {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 4 + lr;
                         sts128(stg + (uint32_t)r * 128u + (uint32_t)((lq ^ (r & 7)) << 4), g[it].x, g[it].y, g[it].z, g[it].w);
                     }
                     __syncwarp();
-                    if (c + 1 < KMAX / 32) {
+                    if (c + 1 < AW / 32) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it)
-                            g[it] = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(it * 4 + lr) * p.ld) + (c + 1) * 8 + lq);
+                            g[it] = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(it * 4 + lr) * p.ld_bytes) + (c + 1) * 8 + lq);
                     }
                     uint32_t r[32];
 #pragma unroll
@@ -309,10 +322,10 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
                     for (int q = 0; q < 8; ++q) {
                         const float4 b = lds128(nba + 128u * g + 16u * q);
                         const int o = 32 * g + 4 * q;
-                        bm[o] = fmaxf(bm[o], fmaf(2.0f, __uint_as_float(v[g][4 * q]), b.x));
-                        bm[o + 1] = fmaxf(bm[o + 1], fmaf(2.0f, __uint_as_float(v[g][4 * q + 1]), b.y));
-                        bm[o + 2] = fmaxf(bm[o + 2], fmaf(2.0f, __uint_as_float(v[g][4 * q + 2]), b.z));
-                        bm[o + 3] = fmaxf(bm[o + 3], fmaf(2.0f, __uint_as_float(v[g][4 * q + 3]), b.w));
+                        bm[o] = fmaxf(bm[o], fmaf(ksc, __uint_as_float(v[g][4 * q]), b.x));
+                        bm[o + 1] = fmaxf(bm[o + 1], fmaf(ksc, __uint_as_float(v[g][4 * q + 1]), b.y));
+                        bm[o + 2] = fmaxf(bm[o + 2], fmaf(ksc, __uint_as_float(v[g][4 * q + 2]), b.z));
+                        bm[o + 3] = fmaxf(bm[o + 3], fmaf(ksc, __uint_as_float(v[g][4 * q + 3]), b.w));
                     }
                 }
                 }
@@ -356,10 +369,10 @@ gram_knn_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 b = lds128(nba + 128u * g + 16u * q);
-                        const float kq[4] = {fmaf(2.0f, __uint_as_float(v[g][4 * q]), b.x),
-                                             fmaf(2.0f, __uint_as_float(v[g][4 * q + 1]), b.y),
-                                             fmaf(2.0f, __uint_as_float(v[g][4 * q + 2]), b.z),
-                                             fmaf(2.0f, __uint_as_float(v[g][4 * q + 3]), b.w)};
+                        const float kq[4] = {fmaf(ksc, __uint_as_float(v[g][4 * q]), b.x),
+                                             fmaf(ksc, __uint_as_float(v[g][4 * q + 1]), b.y),
+                                             fmaf(ksc, __uint_as_float(v[g][4 * q + 2]), b.z),
+                                             fmaf(ksc, __uint_as_float(v[g][4 * q + 3]), b.w)};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (kq[e] > T0) mgt[e] |= 1u << (4 * q + e);
@@ -698,18 +711,18 @@ knn_exact_rows_kernel(const float *__restrict__ x, int64_t ld, int C, const int3
     }
 }
 
-template <int BN, int STAGES, int KMAX>
-int launch_variant(const float *x_hi, const float *x_lo, int64_t ld, int64_t rows, const KnnParams &p, cudaStream_t st)
+template <int BN, int STAGES, int KMAX, bool H>
+int launch_variant(const void *x_hi, const void *x_lo, int64_t ld, int64_t rows, const KnnParams &p, cudaStream_t st)
 {
     using S = KnnSmem<BN, STAGES, KMAX>;
     static_assert(S::TOTAL <= 232448, "shared memory budget exceeded");
     IQ_CHECK(p.K == KMAX, "knn_features_tc: feature width does not match the kernel variant");
     CUtensorMap mbhi, mblo;
-    if (int rc = make_map(&mbhi, x_hi, rows, p.K, ld, BN)) return rc;
-    if (int rc = make_map(&mblo, x_lo, rows, p.K, ld, BN)) return rc;
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gram_knn_kernel<BN, STAGES, KMAX>), S::TOTAL)) return rc;
+    if (int rc = make_map_any(&mbhi, x_hi, rows, p.K, ld, BN, H ? 2 : 4)) return rc;
+    if (int rc = make_map_any(&mblo, x_lo, rows, p.K, ld, BN, H ? 2 : 4)) return rc;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gram_knn_kernel<BN, STAGES, KMAX, H>), S::TOTAL)) return rc;
     const int grid = std::min(p.num_units, sm_count());
-    gram_knn_kernel<BN, STAGES, KMAX><<<grid, KNN_THREADS, S::TOTAL, st>>>(mbhi, mblo, p);
+    gram_knn_kernel<BN, STAGES, KMAX, H><<<grid, KNN_THREADS, S::TOTAL, st>>>(mbhi, mblo, p);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;
@@ -724,21 +737,30 @@ bool knn_features_tc_supported(int64_t N, int C, int k)
 
 int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo, int64_t ld, int C, const float *nxx,
                            int nxx_parts, int64_t clouds, int64_t N, int k, uint32_t *masks, int32_t *cnt, int32_t *idx,
-                           cudaStream_t st)
+                           cudaStream_t st, const KnnOperands16 *h16)
 {
     IQ_CHECK(knn_features_tc_supported(N, C, k), "knn_features_tc: unsupported shape");
     IQ_CHECK(ld % 4 == 0, "knn_features_tc: leading dimension must be a multiple of 4");
+    IQ_CHECK(!h16 || (h16->hi && h16->lo && h16->ld % 8 == 0 && h16->scale > 0.0f), "knn_features_tc: bad fp16 operands");
     const int64_t rows = clouds * N;
     if (rows == 0) return 0;
     IQ_CHECK(rows < (int64_t)1 << 31, "knn_features_tc: too many rows");
     KnnParams p;
     p.K = C; p.points = (int)N; p.m_tiles = (int)(N / TBM); p.num_units = (int)(clouds * p.m_tiles);
-    p.nxx = nxx; p.nxx_parts = nxx_parts; p.masks = masks; p.x_hi = x_hi; p.x_lo = x_lo; p.ld = ld;
+    p.nxx = nxx; p.nxx_parts = nxx_parts; p.masks = masks;
     p.dbg = env_int("IQ_KNN_DBG", 0);
     {
         ProfileScope _ps(C <= 64 ? "tc_gram_knn_c64" : "tc_gram_knn_c128", st);
-        int rc = C == 64 ? launch_variant<128, 5, 64>(x_hi, x_lo, ld, rows, p, st)
-                         : launch_variant<128, 5, 128>(x_hi, x_lo, ld, rows, p, st);
+        int rc;
+        if (h16) {                                                   // nominate on kind::f16 MMAs over the fp16 pair of s * x
+            p.x_hi = h16->hi; p.x_lo = h16->lo; p.ld_bytes = h16->ld * 2; p.key_scale = 2.0f / (h16->scale * h16->scale);
+            rc = C == 64 ? launch_variant<128, 5, 64, true>(h16->hi, h16->lo, h16->ld, rows, p, st)
+                         : launch_variant<128, 5, 128, true>(h16->hi, h16->lo, h16->ld, rows, p, st);
+        } else {
+            p.x_hi = x_hi; p.x_lo = x_lo; p.ld_bytes = ld * 4; p.key_scale = 2.0f;
+            rc = C == 64 ? launch_variant<128, 5, 64, false>(x_hi, x_lo, ld, rows, p, st)
+                         : launch_variant<128, 5, 128, false>(x_hi, x_lo, ld, rows, p, st);
+        }
         if (rc) return rc;
     }
     {

@@ -37,16 +37,22 @@ struct Dense {
     float *w = nullptr;
     float *b = nullptr;
     float *w_hi = nullptr, *w_lo = nullptr;   // tf32 hi/lo split of w for the tcgen05 path
+    __half *w_h_hi = nullptr, *w_h_lo = nullptr;   // optional: two-term fp16 split of w * h_scale (kind::f16 products)
+    float h_scale = 1.0f;
     int cout = 0, cin = 0;
 };
 
 // tf32 hi/lo split on the host (same rounding as split_tf32_kernel)
 void split_tf32_host(const std::vector<float> &w, std::vector<float> &hi, std::vector<float> &lo);
+// two-term fp16 split (common.cuh, split_f16) of w * scale, scale = the power of two that brings max|w| into [2^9, 2^10):
+// far from the fp16 overflow, and the low terms stay normal numbers down to |w| = 2^-12 max|w|
+float split_f16_host(const std::vector<float> &w, std::vector<__half> &hi, std::vector<__half> &lo);
 
 struct DeviceArena {              // owns every device buffer of a model
     std::vector<void *> ptrs;
     ~DeviceArena();
     int upload(const std::vector<float> &host, float **dev);
+    int upload_bytes(const void *host, size_t bytes, void **dev);
 };
 
 class Model {

@@ -3,7 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <mutex>
 
 #include "model.cuh"
@@ -108,17 +110,34 @@ int profile_report(const char **names, double *ms, long long *counts, int cap)
     return n;
 }
 
+int f16_paths()
+{
+    int m = 0;
+    if (env_int("IQ_F16_CONV5", (F16_DEFAULT_PATHS & F16_CONV5) ? 1 : 0)) m |= F16_CONV5;
+    if ((m & F16_CONV5) && env_int("IQ_F16_STORE", (F16_DEFAULT_PATHS & F16_STORE) ? 1 : 0)) m |= F16_STORE;
+    if ((m & F16_CONV5) && env_int("IQ_F16_GRAM", (F16_DEFAULT_PATHS & F16_GRAM) ? 1 : 0)) m |= F16_GRAM;
+    return m;
+}
+
 DeviceArena::~DeviceArena()
 {
     for (void *p : ptrs) cudaFree(p);
 }
 
+int DeviceArena::upload_bytes(const void *host, size_t bytes, void **dev)
+{
+    void *p = nullptr;
+    IQ_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    ptrs.push_back(p);
+    IQ_CUDA(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+    *dev = p;
+    return 0;
+}
+
 int DeviceArena::upload(const std::vector<float> &host, float **dev)
 {
     void *p = nullptr;
-    IQ_CUDA(cudaMalloc(&p, sizeof(float) * std::max<size_t>(host.size(), 1)));
-    ptrs.push_back(p);
-    IQ_CUDA(cudaMemcpy(p, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
+    if (int rc = upload_bytes(host.data(), sizeof(float) * host.size(), &p)) return rc;
     *dev = reinterpret_cast<float *>(p);
     return 0;
 }
@@ -179,6 +198,22 @@ void split_tf32_host(const std::vector<float> &w, std::vector<float> &hi, std::v
         hi[i] = rnd(w[i]);
         lo[i] = rnd(w[i] - hi[i]);
     }
+}
+
+float split_f16_host(const std::vector<float> &w, std::vector<__half> &hi, std::vector<__half> &lo)
+{
+    float mx = 0.0f;
+    for (float v : w) mx = std::max(mx, std::fabs(v));
+    float scale = 1.0f;
+    if (mx > 0.0f && std::isfinite(mx)) {
+        int e = 0;
+        frexpf(mx, &e);                                 // mx = f * 2^e, f in [0.5, 1)
+        scale = ldexpf(1.0f, std::min(std::max(10 - e, -60), 60));
+    }
+    hi.resize(w.size());
+    lo.resize(w.size());
+    for (size_t i = 0; i < w.size(); ++i) split_f16(w[i], scale, hi[i], lo[i]);
+    return scale;
 }
 
 Model::~Model()

@@ -99,6 +99,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// fp16 operands (K = 16 per instruction: the same 32 bytes of a 128B-swizzled row as 8 tf32), fp32 accumulation; twice the
+// tf32 rate.  Used with operands split into two fp16 terms (tc::split_f16): 22 significand bits like the tf32 pair.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -184,6 +195,18 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+// the same for fp16 operands: the A tile in TMEM holds two consecutive-k fp16 values per 32-bit column (lower k in the
+// lower half), so one k-step of 16 elements spans 8 columns -- like 8 tf32
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
 // shared -> global tensor store (bulk async group) and its fences
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
 {
@@ -220,6 +243,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 }
 
+// the same with a/b format F16 = 0 (kind::f16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n)
+{
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+}
+
 __device__ __forceinline__ float tf32_round(float x)
 {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
@@ -247,28 +276,34 @@ inline EncodeTiledFn encode_fn()
 // small per-thread table keyed by everything that goes into them (cuTensorMapEncodeTiled is pure host work, but seven
 // calls per GEMM launch add up over ~100 tensor-core launches per step).
 struct MapKey {
-    const void *base; int64_t rows, ld; int K, box_rows;
-    bool operator==(const MapKey &o) const { return base == o.base && rows == o.rows && ld == o.ld && K == o.K && box_rows == o.box_rows; }
+    const void *base; int64_t rows, ld; int K, box_rows, esize;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && rows == o.rows && ld == o.ld && K == o.K && box_rows == o.box_rows && esize == o.esize;
+    }
 };
 struct MapSlot { MapKey key; CUtensorMap map; bool used; };
 constexpr int MAP_CACHE = 256;                                  // direct-mapped; a collision just re-encodes
 
-inline int make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int64_t ld, int box_rows)
+// esize = 4: fp32 / tf32 elements, 32 per box row; esize = 2: fp16 elements, 64 per box row (128 bytes either way)
+inline int make_map_any(CUtensorMap *map, const void *base, int64_t rows, int K, int64_t ld, int box_rows, int esize)
 {
     static thread_local MapSlot cache[MAP_CACHE] = {};
-    const MapKey key{base, rows, ld, K, box_rows};
+    const MapKey key{base, rows, ld, K, box_rows, esize};
     uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
-    h ^= (uint64_t)rows * 0x9E3779B97F4A7C15ull + (uint64_t)ld * 0xC2B2AE3D27D4EB4Full + (uint64_t)K * 1315423911ull + (uint64_t)box_rows;
+    h ^= (uint64_t)rows * 0x9E3779B97F4A7C15ull + (uint64_t)ld * 0xC2B2AE3D27D4EB4Full + (uint64_t)K * 1315423911ull +
+         (uint64_t)box_rows + (uint64_t)esize * 77u;
     MapSlot &slot = cache[(h ^ (h >> 29)) % MAP_CACHE];
     if (slot.used && slot.key == key) { *map = slot.map; return 0; }
     EncodeTiledFn fn = encode_fn();
     IQ_CHECK(fn != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
-    IQ_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0, "gemm_tc: operand must be 16-byte aligned");
+    IQ_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * esize) % 16 == 0, "gemm_tc: operand must be 16-byte aligned");
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+    const CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IQ_CHECK(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -276,6 +311,10 @@ inline int make_map(CUtensorMap *map, const float *base, int64_t rows, int K, in
     slot.map = *map;
     slot.used = true;
     return 0;
+}
+inline int make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int64_t ld, int box_rows)
+{
+    return make_map_any(map, base, rows, K, ld, box_rows, 4);
 }
 
 inline int sm_count()

@@ -232,7 +232,8 @@ def topk_rows(keys, k, largest=True):
 
 
 def linear(x, w, b=None, act=0, engine=0):
-    """act(x @ w.T + b) through the library's GEMM (engine 0: exact fp32 SIMT, 1: tcgen05 3xTF32)."""
+    """act(x @ w.T + b) through the library's GEMM (engine 0: exact fp32 SIMT, 1: tcgen05 3xTF32, 2: tcgen05 kind::f16 on
+    two-term fp16 splits)."""
     _chk(x, torch.float32, "x")
     _chk(w, torch.float32, "w")
     M, K = x.shape

@@ -6,8 +6,8 @@ bytes per launch (same averaging), plus a launch-list table with each family's s
 import csv, io, json, re, sys
 from collections import defaultdict
 
-FAMILY = [(r"gemm_tc_kernel<128, 3, 1>", "tc_conv5_pool"), (r"gemm_tc_kernel<128, 3, 0>", "tc_edge_pq"),
-          (r"gram_knn_kernel<128, 5, 64>", "tc_gram_knn_c64"), (r"gram_knn_kernel<128, 5, 128>", "tc_gram_knn_c128"),
+FAMILY = [(r"gemm_tc_kernel<128, 3, 1[,>]", "tc_conv5_pool"), (r"gemm_tc_kernel<128, 3, 0[,>]", "tc_edge_pq"),
+          (r"gram_knn_kernel<128, 5, 64[,>]", "tc_gram_knn_c64"), (r"gram_knn_kernel<128, 5, 128[,>]", "tc_gram_knn_c128"),
           (r"knn_rerank_mask_kernel", "knn_rerank"), (r"gather_max_smem_kernel", "gather_max"), (r"knn_xyz_kernel", "knn_xyz"),
           (r"sgemm_kernel", "sgemm_edge_pq"), (r"mask_shapley_kernel", "mask_shapley"), (r"collapse_count_kernel", "collapse_count"),
           (r"collapse_compact_kernel", "collapse_compact"), (r"reward_kernel", "reward"),
@@ -34,7 +34,11 @@ for i, m in per.items():
     a[0] += 1
     a[1] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
     a[2] += m.get("gpu__time_duration.sum", 0.0)
+is_f16 = lambda rx: any(re.search(rx + r", (true|1|\(bool\)1)>", n) for n in names.values())
+f16_paths = (1 if is_f16(r"gemm_tc_kernel<128, 3, 1") else 0) | (2 if is_f16(r"gemm_tc_kernel<128, 3, 0") else 0) | \
+            (4 if is_f16(r"gram_knn_kernel<128, 5, 64") else 0)
 out = {"workload": "dgcnn_k20_shapley_100perm_x33clouds_N1024_R32",
+       "f16_paths": f16_paths,
        "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
                   "--profile-from-start off python scripts/profile_step.py",
        "note": "one step (100 permutations x 33 clouds, collapsed), averages over the step's launches of each kernel; kernel "

@@ -70,6 +70,108 @@ def test_pool_epilogue_vs_float64(clouds, points, N, K, engine):
     assert int(arg.min()) >= 0 and int(arg.max()) < points
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 8), (1024, 256, 64), (4096, 512, 128), (2048, 1024, 512),
+                                   (128 * 149, 128, 96), (200, 256, 264), (1, 128, 64), (128 * 3 + 127, 384, 136)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_f16_split_store_vs_float64(M, N, K, act):
+    """kind::f16 MMAs on two-term fp16 splits of the scaled operands (engine 2, the form conv5 runs in): the same
+    fp32-noise bar as 3xTF32, including ragged row tiles and K tails of the 64-element ring stage."""
+    rs = np.random.RandomState(M + N + K)
+    x = (rs.normal(size=(M, K)) * rs.uniform(0.1, 4.0, size=(1, K))).astype(np.float32)
+    w = rs.normal(size=(N, K)).astype(np.float32)
+    b = rs.normal(size=(N,)).astype(np.float32)
+    want = torch.from_numpy(x).double() @ torch.from_numpy(w).double().T + torch.from_numpy(b).double()
+    if act == 2:
+        want = torch.nn.functional.leaky_relu(want, 0.2)
+    want = want.numpy()
+    got = ops.linear(cu(x), cu(w), cu(b), act=act, engine=2).cpu().numpy()
+    got_tf32 = ops.linear(cu(x), cu(w), cu(b), act=act, engine=1).cpu().numpy()
+    scale = np.abs(want).max()
+    e16, e32 = np.abs(got - want).max() / scale, np.abs(got_tf32 - want).max() / scale
+    print("f16x2 %.2e  3xtf32 %.2e of scale (M %d N %d K %d)" % (e16, e32, M, N, K))
+    assert e16 <= 1e-5, (e16, e32)
+
+
+@pytest.mark.parametrize("magnitude,bar", [(1e-3, 1e-5), (1e-5, 1e-3), (1500.0, 1e-5), (3500.0, 2e-3)])
+def test_f16_split_range(magnitude, bar):
+    """Range behaviour of the fp16 split (activations are stored as fp16 pairs of 8 x): small values lose only their low
+    term to the fp16 subnormal spacing (absolute error 4e-9), values beyond 8188 saturate the high term and degrade
+    gracefully up to 16376 -- never an infinity."""
+    rs = np.random.RandomState(7)
+    x = (rs.normal(size=(256, 128)) * magnitude).astype(np.float32)
+    x = np.clip(x, -16000.0, 16000.0)
+    w = rs.normal(size=(128, 128)).astype(np.float32)
+    want = x.astype(np.float64) @ w.astype(np.float64).T
+    got = ops.linear(cu(x), cu(w), None, engine=2).cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max() / np.abs(want).max()
+    print("|x| ~ %g: %.2e of scale" % (magnitude, err))
+    assert err <= bar
+
+
+@pytest.mark.parametrize("clouds,points,N,K", [(1, 128, 128, 32), (3, 1024, 1024, 512), (5, 2048, 256, 128),
+                                               (160, 1024, 128, 64), (7, 384, 1000, 512)])
+def test_f16_split_pool_vs_float64(clouds, points, N, K):
+    rs = np.random.RandomState(clouds + points + N + K)
+    x = rs.normal(size=(clouds * points, K)).astype(np.float32)
+    x[points // 2:points // 2 + 40] = x[0]
+    w = rs.normal(size=(N, K)).astype(np.float32)
+    b = rs.normal(size=(N,)).astype(np.float32)
+    y = torch.nn.functional.leaky_relu(torch.from_numpy(x).double() @ torch.from_numpy(w).double().T
+                                       + torch.from_numpy(b).double(), 0.2).view(clouds, points, N)
+    mx, mean, arg = ops.linear_pool(cu(x), cu(w), cu(b), clouds, points, act=2, engine=2, want_arg=True)
+    scale = float(y.abs().max())
+    assert np.abs(mx.cpu().numpy() - y.max(1)[0].numpy()).max() / scale <= 1e-5
+    assert np.abs(mean.cpu().numpy() - y.mean(1).numpy()).max() / scale <= 1e-5
+    picked = torch.gather(y, 1, arg.cpu().view(clouds, 1, N)).squeeze(1).numpy()
+    assert np.abs(picked - y.max(1)[0].numpy()).max() / scale <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["dgcnn", "gcnn"])
+def test_f16_paths_equal_3xtf32(name):
+    """The kind::f16 forms of conv5, of the tcgen05 EdgeConv products and of the Gram kNN nomination (IQ_F16_CONV5 /
+    IQ_F16_STORE / IQ_F16_GRAM) against the all-3xTF32 forward on masked clouds, plain and collapsed.  Nothing upstream of a
+    kNN decision changes (the nomination is re-ranked exactly either way), so the logits agree to fp32 noise."""
+    import os
+    import types
+    from interpret_quality_b200 import _lib, synthetic
+    from interpret_quality_b200.tools import final_util
+    from oracle import coalition, geom
+    a = types.SimpleNamespace(model=name, k=20, dataset="shapenet", device=DEV)
+    model = final_util.build_model(a, synthetic.make_state_dict(name))
+    data = synthetic.make_cloud(1024)
+    rid = geom.region_id(data[0], geom.fps(data, 32)[0])
+    center = coalition.center_of(data)
+    masked = geom.mask_shapley(data[0], center, synthetic.make_orders(2, 32), rid)
+    x = cu(masked)
+    keys = ("IQ_F16_CONV5", "IQ_F16_STORE", "IQ_F16_GRAM")
+
+    def run(bits, collapsed):
+        before = {key: os.environ.get(key) for key in keys}
+        for i, key in enumerate(keys):
+            os.environ[key] = "1" if bits & (1 << i) else "0"
+        _lib.load().iq_debug_reload_env()
+        try:
+            assert _lib.f16_paths() == bits
+            masked_to = cu(np.asarray(center, dtype=np.float32).reshape(3)) if collapsed else None
+            return model.forward_point_major(x, masked_to=masked_to).cpu().numpy()
+        finally:
+            for key, val in before.items():
+                if val is None:
+                    del os.environ[key]
+                else:
+                    os.environ[key] = val
+            _lib.load().iq_debug_reload_env()
+
+    for collapsed in (False, True):
+        base = run(0, collapsed)
+        scale = np.abs(base).max()
+        for bits in (1, 3, 5, 7):
+            err = np.abs(run(bits, collapsed) - base).max() / scale
+            print("%s %s f16 paths %d vs 3xtf32: %.2e of scale" % (name, "collapsed" if collapsed else "plain", bits, err))
+            assert err <= 1e-5, (bits, err)                      # two fp32-noise evaluations: measured 3e-6 ... 4e-6
+
+
 def test_batched_gram_keys_through_dgcnn_engine_switch():
     """Same DGCNN forward through both engines: logits agree to fp32 noise, so the kNN graphs agree."""
     import types
