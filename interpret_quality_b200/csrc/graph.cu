@@ -418,7 +418,9 @@ gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__r
 // the L2 -> SM path.  Here a CTA owns (cloud, 32-channel slice, range of points): the slice of P for ALL points of the
 // cloud (N x 128 B) is copied once into shared memory with cp.async and the k gathers per point become LDS.128 -- 8
 // lanes per point read one 128-byte row, so every quarter-warp access is conflict free.
-constexpr int GMS_THREADS = 1024;             // one CTA per SM (the table fills shared memory): all the warps it can hold
+// GMS_THREADS = 1024 for clouds whose table fills most of an SM's shared memory (one CTA per SM: all the warps it can hold);
+// 512 for small (collapsed) clouds, so that three or four CTAs share an SM and one CTA's table fill overlaps the others' gathers.
+template <int GMS_THREADS>
 __global__ void __launch_bounds__(GMS_THREADS)
 gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int N, int k, int Cout,
                        int psplit, int act, float *__restrict__ out, int64_t ldo, float *__restrict__ out_hi,
@@ -635,14 +637,20 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
     if (smem <= 200 * 1024 && N % 128 == 0 && B * (Cout / 32) * 8 < ((int64_t)1 << 31)) {
         {
             ProfileScope _ps("gather_max", st);
-            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gather_max_smem_kernel), 200 * 1024)) return rc;
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gather_max_smem_kernel<1024>), 200 * 1024)) return rc;
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(&gather_max_smem_kernel<512>), 200 * 1024)) return rc;
             const int64_t base_units = B * (Cout / 32);
             int psplit = 1;
             while (psplit < 4 && base_units * psplit < 120) psplit *= 2;   // fill the SMs, but keep the units fat
             // the caller can take per-slice partial squared norms (sq_parts != null: |x_i|^2 = sum of Cout/32 parts)
             float *parts = (neg_sqnorm && sq_parts) ? neg_sqnorm : nullptr;
-            gather_max_smem_kernel<<<(unsigned)(base_units * psplit), GMS_THREADS, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
-                                                                                       act, out, ldo, out_hi, out_lo, parts, h_hi, h_lo, ldh, hscale);
+            // IQ_GM_SMALL (experiment, default off): clouds of <= this many points take the 512-thread form
+            if (N <= env_int("IQ_GM_SMALL", 0))
+                gather_max_smem_kernel<512><<<(unsigned)(base_units * psplit), 512, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
+                                                                                      act, out, ldo, out_hi, out_lo, parts, h_hi, h_lo, ldh, hscale);
+            else
+                gather_max_smem_kernel<1024><<<(unsigned)(base_units * psplit), 1024, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
+                                                                                        act, out, ldo, out_hi, out_lo, parts, h_hi, h_lo, ldh, hscale);
             IQ_COUNT_LAUNCH();
             IQ_LAUNCH_CHECK();
             if (parts) *sq_parts = Cout / 32;
