@@ -45,6 +45,7 @@ constexpr int KNN_EPI_THREADS = 256;
 constexpr int KNN_NOM = 24;                     // columns nominated per row (>= k + slack for 3xTF32 key noise)
 constexpr int XCH_STRIDE = KNN_NOM + 1;         // padded row of the threshold exchange (bank-conflict free)
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int RERANK_F2_DEFAULT = 0;            // packed fp32 distance evaluation in the re-rank's fast path (IQ_RERANK_F2)
 
 struct KnnParams {
     int K;                 // feature width (multiple of 4; TMA zero-fills up to the next multiple of 32)
@@ -453,7 +454,7 @@ __device__ __forceinline__ int warp_inclusive_scan(int x, int lane)
 // instruction), so a warp evaluates 32/LPC candidates at a time with all loads of four such steps in flight; the usual
 // case of <= 32 candidates is then ordered by a 15-step bitonic network over the lanes, keyed by (float64 distance,
 // index).
-template <int C>
+template <int C, bool F2>
 __global__ void __launch_bounds__(256, 4)
 knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *__restrict__ masks, int64_t rows, int N,
                        int k, int32_t *__restrict__ idx, int32_t *__restrict__ cnt)
@@ -532,11 +533,28 @@ knn_rerank_mask_kernel(const float *__restrict__ x, int64_t ld, const uint32_t *
             for (int u = 0; u < 2; ++u) {
                 float acc = 0.0f;
                 if (live[u]) {
+                    if (F2) {
+                        // packed fp32 (FADD2 / FFMA2): a scalar fp32 op issues every second cycle per scheduler on sm_100, and
+                        // this loop is the kernel's fp32 work.  Two chains (even / odd channels) summed at the end: the same
+                        // order for every candidate, so coincident points still give bit-equal distances.
+                        unsigned long long a2 = 0ull;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float d0 = xi[q].x - b[u][q].x, d1 = xi[q].y - b[u][q].y;
-                        const float d2 = xi[q].z - b[u][q].z, d3 = xi[q].w - b[u][q].w;
-                        acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned long long d01 = sub_f2(pack_f2(xi[q].x, xi[q].y), pack_f2(b[u][q].x, b[u][q].y));
+                            const unsigned long long d23 = sub_f2(pack_f2(xi[q].z, xi[q].w), pack_f2(b[u][q].z, b[u][q].w));
+                            a2 = fma_f2(d01, d01, a2);
+                            a2 = fma_f2(d23, d23, a2);
+                        }
+                        float lo, hi;
+                        unpack_f2(a2, lo, hi);
+                        acc = lo + hi;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float d0 = xi[q].x - b[u][q].x, d1 = xi[q].y - b[u][q].y;
+                            const float d2 = xi[q].z - b[u][q].z, d3 = xi[q].w - b[u][q].w;
+                            acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+                        }
                     }
 #pragma unroll
                     for (int o = LPC / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
@@ -766,8 +784,11 @@ int launch_knn_features_tc(const float *x, const float *x_hi, const float *x_lo,
     {
         ProfileScope _ps("knn_rerank", st);
         const unsigned grid = (unsigned)ceil_div(rows * 32, 256);
-        if (C == 64) knn_rerank_mask_kernel<64><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
-        else knn_rerank_mask_kernel<128><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        const bool f2 = env_int("IQ_RERANK_F2", RERANK_F2_DEFAULT) != 0;
+        if (C == 64 && f2) knn_rerank_mask_kernel<64, true><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        else if (C == 64) knn_rerank_mask_kernel<64, false><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        else if (f2) knn_rerank_mask_kernel<128, true><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
+        else knn_rerank_mask_kernel<128, false><<<grid, 256, 0, st>>>(x, ld, masks, rows, (int)N, k, idx, cnt);
         IQ_COUNT_LAUNCH();
         IQ_LAUNCH_CHECK();
         const unsigned scan_grid = (unsigned)std::min<int64_t>(ceil_div(rows, 32 * 8), 4 * sm_count());

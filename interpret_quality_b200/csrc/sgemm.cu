@@ -11,6 +11,13 @@
 // 4x4 so that shared-memory float4 reads are conflict free; register-staged
 // double buffering, one __syncthreads per k-tile.
 //
+// The inner product runs on packed fp32 FMAs (fma.rn.f32x2 -> FFMA2, sm_100): a
+// scalar FFMA issues every second cycle per scheduler on this part, so 64 of
+// them per k-step cap the kernel at half the fp32 rate; 32 FFMA2 (a[i] broadcast
+// x two adjacent columns of b) do the same work.  Each half of an FFMA2 is an
+// IEEE fp32 fma and every output keeps its own k-ordered chain, so the results
+// are bit-identical to the scalar form (IQ_SGEMM_F2=0 runs that form).
+//
 // Epilogues:
 //   store          C[m][n] = act(alpha*acc + bias[n] + row_bias[m / row_group][n])
 //   pool           per 128-row tile: column max (+ lowest-index argmax) and column
@@ -25,6 +32,7 @@ namespace iq {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 8, LDS = BM + 4;
+constexpr int SGEMM_F2_DEFAULT = 0;
 
 template <bool kVec>
 __device__ __forceinline__ void load_tile(const float *__restrict__ P, int64_t ld, int rows, int K, int r0, int k0,
@@ -55,8 +63,8 @@ __device__ __forceinline__ void store_tile(float (*S)[LDS], int tid, const float
     for (int j = 0; j < 4; ++j) S[kq + j][row] = reg[j];
 }
 
-template <bool kVec>
-__global__ void __launch_bounds__(256)
+template <bool kVec, bool F2>
+__global__ void __launch_bounds__(256, 2)
 sgemm_kernel(const GemmDesc g)
 {
     __shared__ __align__(16) float As[2][BK][LDS];
@@ -67,10 +75,14 @@ sgemm_kernel(const GemmDesc g)
     const float *B = g.B + (int64_t)bz * g.strideB;
 
     float acc[8][8];
+    unsigned long long acc2[8][4];                     // F2: columns (2j, 2j+1) of row i packed as one f32x2 accumulator
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
+    }
 
     float ra[4], rb[4];
     load_tile<kVec>(A, g.lda, g.M, g.K, m0, 0, tid, ra);
@@ -94,16 +106,33 @@ sgemm_kernel(const GemmDesc g)
             const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[cur][k][64 + tx * 4]);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            if (F2) {
+                const unsigned long long bp[4] = {pack_f2(b[0], b[1]), pack_f2(b[2], b[3]), pack_f2(b[4], b[5]), pack_f2(b[6], b[7])};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned long long ap = pack_f2(a[i], a[i]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) acc2[i][j] = fma_f2(ap, bp[j], acc2[i][j]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
         }
         if (kt + 1 < nk) {
             store_tile(As[cur ^ 1], tid, ra);
             store_tile(Bs[cur ^ 1], tid, rb);
         }
         __syncthreads();
+    }
+
+    if (F2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack_f2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
     }
 
     // ---- epilogue
@@ -262,8 +291,11 @@ int launch_sgemm(const GemmDesc &g, cudaStream_t st)
                      (g.strideB % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
     dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)g.batch);
-    if (vec) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
-    else sgemm_kernel<false><<<grid, 256, 0, st>>>(g);
+    const bool f2 = env_int("IQ_SGEMM_F2", SGEMM_F2_DEFAULT) != 0;
+    if (vec && f2) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+    else if (vec) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
+    else if (f2) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
+    else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
     IQ_COUNT_LAUNCH();
     IQ_LAUNCH_CHECK();
     return 0;

@@ -7,9 +7,12 @@ timeout 900 python -m pytest tests -m gpu -q -s > $OUT/v6_gpu_tests.log 2>&1; ec
 grep -E "max\|I\||float64 audit|cloud .*ours-ref|worst logits|vs reference|chain vs|collapsed vs|further than|phi err|N=|f16 paths|f16x2" $OUT/v6_gpu_tests.log > $OUT/v6_parity_numbers.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/v6_bench.json 2> $OUT/v6_bench.err; echo "bench rc=$?"
-for cfg in "IQ_LANES=3" "IQ_GM_SMALL=512" "IQ_GM_SMALL=768"; do
+IQ_RERANK_F2=1 timeout 200 python -m pytest tests/test_gpu_knn_tc.py -q > $OUT/v6_knn_f2.log 2>&1; echo "knn unit (packed re-rank) rc=$?"; tail -1 $OUT/v6_knn_f2.log
+IQ_SGEMM_F2=1 timeout 200 python -m pytest tests/test_gpu_tc_gemm.py -q -k "store_epilogue or pool_epilogue" > $OUT/v6_sgemm_f2.log 2>&1; echo "sgemm unit (packed fma) rc=$?"; tail -1 $OUT/v6_sgemm_f2.log
+for cfg in "IQ_LANES=3" "IQ_GM_SMALL=512" "IQ_SGEMM_F2=1" "IQ_RERANK_F2=1"; do
     env $cfg timeout 200 python bench.py --no-extras --no-cpu-baseline --steps 10 --warmup 3 > $OUT/v6_bench_$cfg.json 2> $OUT/v6_bench_$cfg.err; echo "bench $cfg rc=$?"
 done
+IQ_SGEMM_F2=1 IQ_RERANK_F2=1 timeout 200 python bench.py --no-extras --no-cpu-baseline --steps 10 --warmup 3 > $OUT/v6_bench_IQ_F2_BOTH.json 2> $OUT/v6_bench_IQ_F2_BOTH.err; echo "bench both F2 rc=$?"
 python - <<'PY'
 import json, glob
 def show(fn):
@@ -28,6 +31,3 @@ def show(fn):
 show("gpurun_out/v6_bench.json")
 for fn in sorted(glob.glob("gpurun_out/v6_bench_IQ*.json")): show(fn)
 PY
-python scripts/profile_all_kernels.py dgcnn > $OUT/v6_prof_plain.log 2>&1 || { echo "profile plain run failed"; tail -3 $OUT/v6_prof_plain.log; exit 0; }
-timeout 300 ncu --set full --clock-control none --profile-from-start off -k regex:'gemm_tc_kernel|gram_knn_kernel|gather_max_smem' -f -o /tmp/v6_f16 python scripts/profile_all_kernels.py dgcnn > $OUT/v6_ncu_f16.log 2>&1; echo "ncu capture rc=$?"
-ncu -i /tmp/v6_f16.ncu-rep --page raw --csv > $OUT/v6_f16_raw.csv 2>/dev/null; ls -la /tmp/v6_f16.ncu-rep $OUT/v6_f16_raw.csv

@@ -22,5 +22,9 @@ for f in funcs[1:]:
     out.append("| %s | " % dem[:70] + " | ".join(str(c[k]) for k in keys) + " |")
 out.append("| **whole library (%d kernels)** | " % (len(funcs) - 1) + " | ".join(str(tot[k]) for k in keys) + " |")
 out.append("\nNo `HMMA` (mma.sync / wmma) anywhere: every tensor-core product is a tcgen05 UTCHMMA with TMEM accumulators.")
+out.append("kind::tf32 and kind::f16 are the same SASS opcode: the operand format travels in the instruction descriptor register "
+           "(`idesc[UR..]`).  The kernel variants whose last template argument is `true` (gemm_tc_kernel<128, 3, 0|1, true>, "
+           "gram_knn_kernel<128, 5, 64|128, true>) are built with the F16 descriptor (tc_ptx.cuh::make_idesc_f16) and are the ones "
+           "DGCNN / GCNN run by default (iq_f16_paths() = 7).")
 open(os.path.join(ROOT, "profiles", "sass_tcgen05.txt"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[-3:]))
