@@ -420,7 +420,7 @@ gather_max_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__r
 // lanes per point read one 128-byte row, so every quarter-warp access is conflict free.
 // GMS_THREADS = 1024 for clouds whose table fills most of an SM's shared memory (one CTA per SM: all the warps it can hold);
 // 512 for small (collapsed) clouds, so that three or four CTAs share an SM and one CTA's table fill overlaps the others' gathers.
-constexpr int GM_SMALL_DEFAULT = 512;
+constexpr int GM_SMALL_DEFAULT = 768;
 template <int GMS_THREADS>
 __global__ void __launch_bounds__(GMS_THREADS)
 gather_max_smem_kernel(const float *__restrict__ PQ, int64_t ldpq, const int32_t *__restrict__ idx, int N, int k, int Cout,
@@ -645,8 +645,9 @@ int launch_gather_max(const float *PQ, int64_t ldpq, const int32_t *idx, int64_t
             while (psplit < 4 && base_units * psplit < 120) psplit *= 2;   // fill the SMs, but keep the units fat
             // the caller can take per-slice partial squared norms (sq_parts != null: |x_i|^2 = sum of Cout/32 parts)
             float *parts = (neg_sqnorm && sq_parts) ? neg_sqnorm : nullptr;
-            // clouds of <= GM_SMALL_DEFAULT points (IQ_GM_SMALL overrides) take the 512-thread form: measured +2.4 % on the
-            // headline step at 512 (gather_max 5.53 -> 5.20 ms; the collapsed clouds are mostly small)
+            // clouds of <= GM_SMALL_DEFAULT points (IQ_GM_SMALL overrides) take the 512-thread form: two to four CTAs then share an
+            // SM.  Same box, headline step: threshold 512 / 768 / 1024 -> 123.8k / 126.3k / 123.9k forwards/s (gather_max 5.53 ms
+            // with one form only, 5.17 / 5.05 / 4.97 ms; at 1024 the step loses elsewhere what the kernel gains)
             if (N <= env_int("IQ_GM_SMALL", GM_SMALL_DEFAULT))
                 gather_max_smem_kernel<512><<<(unsigned)(base_units * psplit), 512, smem, st>>>(PQ, ldpq, idx, (int)N, k, Cout, psplit,
                                                                                       act, out, ldo, out_hi, out_lo, parts, h_hi, h_lo, ldh, hscale);
