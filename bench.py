@@ -328,19 +328,19 @@ def kernel_work(model, k, buckets, points=1024, f16=0):
          "collapse_compact": H(12.0 * points * clouds + 12.0 * rows)}
     if model in ("dgcnn", "gcnn"):
         w["tc_conv5_pool"] = T(2.0 * rows * 512 * 1024, 3, "f16" if f16_conv5 else "tf32")
-        w["sgemm_conv5_pool"] = T(2.0 * rows * 512 * 1024, 1)
+        w["sgemm_conv5_pool"] = T(2.0 * rows * 512 * 1024, 1, "fp32-simt")
         couts = (64, 64, 128, 256)
         if model == "dgcnn":
-            w["sgemm_edge_pq"] = T(2.0 * rows * (3 * 128 + 64 * 128 + 64 * 256), 1)
+            w["sgemm_edge_pq"] = T(2.0 * rows * (3 * 128 + 64 * 128 + 64 * 256), 1, "fp32-simt")
             w["tc_edge_pq"] = T(2.0 * rows * 128 * 512, 3, "f16" if f16_store else "tf32")
-            w["sgemm_gram"] = T(2.0 * sq * (64 + 64 + 128), 1)
+            w["sgemm_gram"] = T(2.0 * sq * (64 + 64 + 128), 1, "fp32-simt")
             w["tc_gram_knn_c64"] = T(2.0 * sq * 64 * 2, 6, "f16" if f16_gram else "tf32")   # two layers with 64-wide features
             w["tc_gram_knn_c128"] = T(2.0 * sq * 128, 6, "f16" if f16_gram else "tf32")
             w["topk_rows"] = H(3.0 * (4.0 * sq + 4.0 * rows * k))
             # masks (2 bits per column pair) + the feature rows once + neighbour lists, three layers
             w["knn_rerank"] = H(3.0 * (sq / 4.0 + 4.0 * rows * k) + 4.0 * rows * (64 + 64 + 128))
         else:
-            w["sgemm_edge_pq"] = T(2.0 * rows * 3 * 128, 1)
+            w["sgemm_edge_pq"] = T(2.0 * rows * 3 * 128, 1, "fp32-simt")
             w["tc_edge_pq"] = T(2.0 * rows * (64 * 128 + 64 * 256 + 128 * 512), 3, "f16" if f16_store else "tf32")
         # P|Q rows read once, neighbour lists, the squared norm, and the output in the formats its consumers read
         # (edgeconv_model.cu): fp32 (SIMT products + exact re-rank: DGCNN layers 1-3), the tf32 pair (Gram kNN and tf32
