@@ -43,6 +43,10 @@ int iq_debug_reload_env(void);
  * tcgen05 EdgeConv products, bit 2 the Gram kNN nomination.  Library defaults, overridden by IQ_F16_CONV5 /
  * IQ_F16_STORE / IQ_F16_GRAM = 0 | 1 (bench.py labels its roofline lines with it). */
 int iq_f16_paths(void);
+/* Host half of that operand format (no device needed; CPU tests): the two-term fp16 split the library applies to a weight
+ * matrix -- hi = fp16(s w), lo = fp16(s w - hi) as IEEE binary16 bit patterns, s the power of two that brings max|w| into
+ * [2^9, 2^10) -- so that (hi + lo) / s reproduces w to 2^-22 relative. */
+int iq_split_f16_host(const float *w_host, int64_t n, uint16_t *hi_host, uint16_t *lo_host, float *scale_host);
 
 /* Per-kernel timing for bench.py's roofline leg: while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  iq_profile_report synchronises the device and returns the

@@ -19,6 +19,7 @@ SIGNATURES = {
     "iq_launch_count": (ctypes.c_uint64, []),
     "iq_debug_reload_env": (_int, []),
     "iq_f16_paths": (_int, []),
+    "iq_split_f16_host": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "iq_profile_enable": (_int, [_int]),
     "iq_profile_report": (_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_longlong), _int]),

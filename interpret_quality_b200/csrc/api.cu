@@ -24,6 +24,19 @@ int iq_debug_reload_env(void)
 
 int iq_f16_paths(void) { return f16_paths(); }
 
+int iq_split_f16_host(const float *w, int64_t n, uint16_t *hi, uint16_t *lo, float *scale)
+{
+    IQ_CHECK(w && hi && lo && scale && n >= 0, "iq_split_f16_host: bad argument");
+    std::vector<float> v(w, w + n);
+    std::vector<__half> h, l;
+    *scale = split_f16_host(v, h, l);
+    if (n) {
+        memcpy(hi, h.data(), sizeof(uint16_t) * (size_t)n);
+        memcpy(lo, l.data(), sizeof(uint16_t) * (size_t)n);
+    }
+    return 0;
+}
+
 int iq_profile_enable(int on)
 {
     profile_enable(on != 0);

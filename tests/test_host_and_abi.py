@@ -109,3 +109,56 @@ def test_seed_replay_of_generate_all_orders():
     a = types.SimpleNamespace(num_samples_save=20, num_regions=32)
     orders = generate_all_orders(None, a, save=False)
     assert np.array_equal(orders, synthetic.make_orders(20, 32, seed=1))
+
+
+def test_f16_operand_split_host(lib):
+    """The two-term fp16 split of the kind::f16 tensor-core paths (csrc/common.cuh::split_f16, the host half the library
+    applies to weights): bit patterns equal a numpy restatement, the pair reproduces the value to 2^-22, the scale is the
+    power of two that brings max|w| into [2^9, 2^10), and nothing overflows."""
+    rs = np.random.RandomState(3)
+    for w in (rs.normal(size=4096).astype(np.float32) * 0.05,
+              (rs.normal(size=1000) * rs.uniform(1e-4, 30.0, size=1000)).astype(np.float32),
+              np.array([0.0, -0.0, 1.0, -1.0, 3.0e-6, 123.456], np.float32),
+              np.zeros(7, np.float32)):
+        hi = np.zeros(w.size, np.uint16)
+        lo = np.zeros(w.size, np.uint16)
+        scale = ctypes.c_float(0.0)
+        rc = lib.iq_split_f16_host(w.ctypes.data, w.size, hi.ctypes.data, lo.ctypes.data, ctypes.byref(scale))
+        assert rc == 0
+        s = np.float32(scale.value)
+        mx = np.abs(w).max()
+        if mx > 0:
+            assert 512.0 <= mx * s < 1024.0 and float(np.log2(s)).is_integer()
+        else:
+            assert s == 1.0
+        xs = w * s                                                   # exact: s is a power of two
+        want_hi = xs.astype(np.float16)
+        want_lo = (xs - want_hi.astype(np.float32)).astype(np.float16)
+        assert np.array_equal(hi, want_hi.view(np.uint16)) and np.array_equal(lo, want_lo.view(np.uint16))
+        back = (hi.view(np.float16).astype(np.float64) + lo.view(np.float16).astype(np.float64)) / float(s)
+        assert np.isfinite(back).all()
+        # 22 significand bits while the low term is a normal fp16 number; the fp16 subnormal spacing below that
+        err = np.abs(back - w.astype(np.float64))
+        assert (err <= np.maximum(np.abs(w) * 2.0 ** -22, 2.0 ** -25 / float(s))).all()
+
+
+def test_f16_paths_switches(lib):
+    """iq_f16_paths(): every kind::f16 path on by default; IQ_F16_CONV5=0 switches all of them off (the other two read the
+    fp16 activation buffers conv5's path writes), the other switches only their own path."""
+    keys = ("IQ_F16_CONV5", "IQ_F16_STORE", "IQ_F16_GRAM")
+    before = {k: os.environ.pop(k, None) for k in keys}
+    try:
+        lib.iq_debug_reload_env()
+        assert _lib.f16_paths() == 7
+        for env, want in (({"IQ_F16_CONV5": "0"}, 0), ({"IQ_F16_STORE": "0"}, 5), ({"IQ_F16_GRAM": "0"}, 3),
+                          ({"IQ_F16_STORE": "0", "IQ_F16_GRAM": "0"}, 1)):
+            os.environ.update(env)
+            lib.iq_debug_reload_env()
+            assert _lib.f16_paths() == want, (env, _lib.f16_paths())
+            for k in env:
+                del os.environ[k]
+    finally:
+        for k, v in before.items():
+            if v is not None:
+                os.environ[k] = v
+        lib.iq_debug_reload_env()
