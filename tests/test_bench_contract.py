@@ -44,3 +44,27 @@ def test_config_table_covers_baseline_configs():
         assert half[k][1] <= full[k][1]
     assert abs(half["tc_gram_knn_c64"][1] / full["tc_gram_knn_c64"][1] - 0.25) < 1e-9
     assert abs(half["tc_conv5_pool"][1] / full["tc_conv5_pool"][1] - 0.5) < 1e-9
+
+
+def test_roofline_object_from_a_recorded_kernel_list():
+    """bench.pick_roofline on the per-kernel list of a recorded B200 line (profiles/r2_v7_bench_1gpu.json): the dominant
+    kernel's entry with the contract's keys, and the largest tensor-core kernel beside it when the dominant one is not."""
+    sys.path.insert(0, ROOT)
+    import bench
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r2_v7_bench_1gpu.json")).read().strip().splitlines()[-1])
+    kernels = line["breakdown"]["kernels"]
+    rf = bench.pick_roofline(kernels)
+    assert rf["kernel"] == kernels[0]["kernel"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in rf
+    assert rf["bound"] in ("hbm", "tensor") and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    if rf["bound"] != "tensor":
+        top = rf["top_tensor_kernel"]
+        assert top["kernel"] == "tc_conv5_pool" and top["mma_kind"] == "f16" and 0.25 < top["frac"] < 0.45
+    assert bench.pick_roofline([]) is None
+    json.dumps(rf)
+    # kernel_work labels the formats the library reports (iq_f16_paths bit mask)
+    w7 = bench.kernel_work("dgcnn", 20, {1024: 10}, 1024, 7)
+    w0 = bench.kernel_work("dgcnn", 20, {1024: 10}, 1024, 0)
+    assert w7["tc_conv5_pool"][3] == "f16" and w0["tc_conv5_pool"][3] == "tf32" and w7["sgemm_edge_pq"][3] == "fp32-simt"
+    assert w7["gather_max"][1] < w0["gather_max"][1]                  # no tf32 pair left to write
