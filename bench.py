@@ -84,8 +84,9 @@ def peaks():
     if os.path.exists(fn):
         p = json.load(open(fn))
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
-                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0, "source": "fallback"}
 
 
 def workload_name(c, split=None):
@@ -373,6 +374,53 @@ def kernel_work(model, k, buckets, points=1024, f16=0):
         w["tc_sa_point"] = T(mac((512, 132, 128), (128, 260, 256)))
         w["tc_sa3_linear"] = T(mac((1, 16384, 1024)))
     return w
+
+
+FP32_FMA_LANES_PER_SM, SM_COUNT = 128, 148                 # B200: fp32 FMA peak = 148 SMs x 128 lanes x 2 FLOP x SM clock
+
+
+def kernel_rooflines(rep, work, traffic, pk, tf32):
+    """Per-kernel roofline entries of one profiled step, largest device time first.  rep: {kernel: (ms per step, launches)}
+    from iq_profile_report; work: kernel_work(); traffic: traffic_table(); pk: peaks(); tf32: measure_tf32_peak()."""
+    tot = sum(ms for ms, _ in rep.values())
+    kernels = []
+    for name, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+        if name not in work or n <= 0 or ms <= 0.0:
+            continue
+        bound, per_step, mult, mma_kind = work[name]
+        per_launch = per_step / n
+        dur = ms * 1e-3 / n
+        if bound == "tensor":
+            ach, peak, unit = per_launch / dur / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
+        else:
+            ach, peak, unit = per_launch / dur / 1e9, pk["hbm_gbs"], "GB/s"
+        tr = traffic.get(name)
+        k = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+             "traffic": tr["dram_bytes_per_launch"] if tr else None,
+             "traffic_source": ("profiles/r2_traffic.json: ncu --set full, dram bytes averaged over the %d launches "
+                                "of one step" % tr["launches"]) if tr else None,
+             "avg_launch_ms": dur * 1e3, "launches_per_step": n, "share_of_step": ms / tot,
+             "algorithmic_per_launch": per_launch, "peak_source": pk["source"]}
+        if bound == "tensor":
+            # fp32-grade products cost `mult` MMAs each: the executed rate is what the tensor pipe sees
+            k["mmas_per_logical_mac"] = mult
+            k["mma_kind"] = mma_kind
+            k["executed_tflops"] = ach * mult
+            k["executed_frac_of_tf32_peak"] = k["executed_frac_of_tf32_sustained"] = None
+            if mma_kind == "f16":
+                # two-term fp16 operands: the MMAs run at the bf16 / fp16 rate, the contract's own yardstick
+                k["executed_frac_of_bf16_sustained"] = ach * mult / pk["bf16_tflops_sustained"]
+            elif mma_kind == "fp32-simt":
+                # CUDA-core GEMM (exact fp32 upstream of a dynamic kNN): its own ceiling is the fp32 FMA rate, not the tensor pipe
+                fp32_peak = SM_COUNT * FP32_FMA_LANES_PER_SM * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+                k["frac_of_fp32_fma_peak"] = ach / fp32_peak
+                k["fp32_fma_peak_tflops"] = fp32_peak
+            elif mult > 1 and tf32:
+                # cuBLAS dense TF32 of this run: best-of-10 ("burst") and back-to-back ("sustained", power-capped clocks)
+                k["executed_frac_of_tf32_peak"] = ach * mult / tf32["tf32_tflops"]
+                k["executed_frac_of_tf32_sustained"] = ach * mult / tf32["tf32_tflops_sustained"]
+        kernels.append(k)
+    return kernels
 
 
 def pick_roofline(kernels):
@@ -679,39 +727,7 @@ def run_b200(a):
         if c["kind"] == "shapley":                            # one forward call per profiled step: the buckets describe it
             work = kernel_work(c["model"], 20, buckets, c["points"], rig.lib.f16_paths())
             traffic = traffic_table(workload_name(c), rig.lib.f16_paths())
-            kernels = []
-            for name, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
-                if name not in work:
-                    continue
-                bound, per_step, mult, mma_kind = work[name]
-                per_launch = per_step / n
-                dur = ms * 1e-3 / n
-                if bound == "tensor":
-                    ach, peak, unit = per_launch / dur / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
-                else:
-                    ach, peak, unit = per_launch / dur / 1e9, pk["hbm_gbs"], "GB/s"
-                tr = traffic.get(name)
-                k = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                     "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                     "traffic_source": ("profiles/r2_traffic.json: ncu --set full, dram bytes averaged over the %d launches "
-                                        "of one step" % tr["launches"]) if tr else None,
-                     "avg_launch_ms": dur * 1e3, "launches_per_step": n, "share_of_step": ms / tot,
-                     "algorithmic_per_launch": per_launch, "peak_source": pk["source"]}
-                if bound == "tensor":
-                    # the kernels compute fp32 products as `mult` tf32 MMAs each: the executed rate is what the tensor
-                    # pipe sees, against the dense TF32 rate measured at the start of this leg
-                    k["mmas_per_logical_mac"] = mult
-                    k["mma_kind"] = mma_kind
-                    k["executed_tflops"] = ach * mult
-                    if mma_kind == "f16":
-                        # two-term fp16 operands: the MMAs run at the bf16 / fp16 rate, the contract's own yardstick
-                        k["executed_frac_of_bf16_sustained"] = ach * mult / pk["bf16_tflops_sustained"]
-                        k["executed_frac_of_tf32_peak"] = k["executed_frac_of_tf32_sustained"] = None
-                    else:
-                        # cuBLAS dense TF32 of this run: best-of-10 ("burst") and back-to-back ("sustained", power-capped clocks)
-                        k["executed_frac_of_tf32_peak"] = ach * mult / tf32["tf32_tflops"] if mult > 1 else None
-                        k["executed_frac_of_tf32_sustained"] = ach * mult / tf32["tf32_tflops_sustained"] if mult > 1 else None
-                kernels.append(k)
+            kernels = kernel_rooflines(rep, work, traffic, pk, tf32)
             breakdown["kernels"] = kernels
             roofline = pick_roofline(kernels)
 

@@ -68,3 +68,30 @@ def test_roofline_object_from_a_recorded_kernel_list():
     w0 = bench.kernel_work("dgcnn", 20, {1024: 10}, 1024, 0)
     assert w7["tc_conv5_pool"][3] == "f16" and w0["tc_conv5_pool"][3] == "tf32" and w7["sgemm_edge_pq"][3] == "fp32-simt"
     assert w7["gather_max"][1] < w0["gather_max"][1]                  # no tf32 pair left to write
+
+
+def test_kernel_rooflines_reproduce_a_recorded_line():
+    """bench.kernel_rooflines fed with the recorded per-kernel times and evaluated-cloud buckets of a B200 run reproduces
+    that run's roofline fractions (the arithmetic of the roofline leg, checked without a GPU)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r2_v7_bench_1gpu.json")).read().strip().splitlines()[-1])
+    bd = line["breakdown"]
+    rep = {k: (v["ms"], v["launches"]) for k, v in bd["by_kernel"].items()}
+    buckets = {int(n): c for n, c in bd["evaluated_clouds_by_points"].items()}
+    work = bench.kernel_work("dgcnn", 20, buckets, 1024, 7)
+    pk = bench.peaks()
+    got = bench.kernel_rooflines(rep, work, {}, pk, line["tf32_peak"])
+    want = {k["kernel"]: k for k in bd["kernels"]}
+    assert [k["kernel"] for k in got][:3] == [k["kernel"] for k in bd["kernels"]][:3]
+    for k in got:
+        w = want[k["kernel"]]
+        ms = rep[k["kernel"]][0]                                       # recorded rounded to 1 us: that much slack on the ratio
+        assert abs(k["frac"] - w["frac"]) <= (6e-4 / ms + 1e-3) * w["frac"] + 1e-9, k["kernel"]
+        assert k["bound"] == w["bound"] and k["launches_per_step"] == w["launches_per_step"]
+    conv5 = next(k for k in got if k["kernel"] == "tc_conv5_pool")
+    assert conv5["mma_kind"] == "f16" and abs(conv5["executed_frac_of_bf16_sustained"] - 3 * conv5["frac"]) < 1e-12
+    simt = next(k for k in got if k["kernel"] == "sgemm_edge_pq")
+    assert simt["mma_kind"] == "fp32-simt" and 0.2 < simt["frac_of_fp32_fma_peak"] < 0.6
+    json.dumps(got)
+    assert bench.kernel_rooflines({}, work, {}, pk, None) == []
