@@ -243,7 +243,8 @@ int iq_region_smoothness_epoch(float *data_dev, const float *data_orig_dev, cons
                                int mode, int rising, double step, double enum_step, double dist_threshold,
                                double stop_ratio, int max_iteration, int clamp, void *stream);
 
-/* GEMM engine of the masked forward: 1 = tcgen05 3xTF32 (default), 0 = exact fp32 SIMT. */
+/* GEMM engine of the masked forward: 1 = tcgen05 on two-term operand splits (default: fp16 pairs on kind::f16 for the
+ * DGCNN / GCNN products iq_f16_paths() reports, 3xTF32 pairs elsewhere), 0 = exact fp32 SIMT everywhere. */
 int iq_model_set_engine(iq_model *m, int engine);
 
 #ifdef __cplusplus

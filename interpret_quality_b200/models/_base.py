@@ -127,7 +127,8 @@ class IQModule(nn.Module):
         self._ws = None
 
     def set_engine(self, engine):
-        """GEMM engine of the forward pass: "3xtf32" (tcgen05, default) or "fp32" (exact SIMT)."""
+        """GEMM engine of the forward pass: "3xtf32" / "tc" (tcgen05 on two-term operand splits -- fp16 pairs for the DGCNN /
+        GCNN tensor products, tf32 pairs elsewhere; default) or "fp32" (exact SIMT)."""
         self._set_knob("engine", {"3xtf32": 1, "tc": 1, "fp32": 0, "simt": 0}[engine], _lib.load().iq_model_set_engine)
 
     def set_chunk(self, chunk):
